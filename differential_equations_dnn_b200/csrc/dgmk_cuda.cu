@@ -1,0 +1,208 @@
+// CUDA backend (sm_100a) + the extern "C" surface of include/dgmk.h.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
+//        --expt-relaxed-constexpr -Xcompiler -fPIC -shared -o libdgmk.so dgmk_cuda.cu
+// This is the only implementation the package loads: there is no CPU path.
+#include <cuda_runtime.h>
+#include "dgmk_capi_impl.h"
+#include "dgmk_gemm.cuh"
+
+namespace dgmk {
+
+constexpr int EW_THREADS = 256;
+
+template <class F>
+__global__ void __launch_bounds__(EW_THREADS) ew_kernel(const F f, int64_t n) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
+}
+
+// deterministic second stage: out[i] (+)= sum_s part[s][i], FP64 accumulate, fixed order
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int nparts, int64_t n,
+                                                              float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int p = 0; p < nparts; ++p) s += (double)part[(int64_t)p * n + i];
+  out[i] += (float)s;
+}
+
+// out-partials[blk][e][n] = sum_{r in block's row strip} Wt[r][e] * Mat[r][n]
+// grid = (ceil(N / 128), nblk); thread = one column n, 4 weighted sums.
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(128) wcolsum_kernel(const float* __restrict__ Mat, int64_t ldm, int N,
+                                                      const float* __restrict__ Wt, int64_t M, int64_t rows_per_blk,
+                                                      float* __restrict__ part) {
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_blk;
+  const int64_t r1 = (r0 + rows_per_blk < M) ? r0 + rows_per_blk : M;
+  constexpr int NE = WEIGHTED ? 4 : 1;
+  float acc[NE];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) acc[e] = 0.f;
+  __shared__ float4 wsm[128];
+  for (int64_t rb = r0; rb < r1; rb += 128) {
+    int cnt = (int)((r1 - rb < 128) ? r1 - rb : 128);
+    if (WEIGHTED) {
+      __syncthreads();
+      if (threadIdx.x < cnt) wsm[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(Wt) + rb + threadIdx.x);
+      __syncthreads();
+    }
+    if (n < N) {
+#pragma unroll 4
+      for (int q = 0; q < cnt; ++q) {
+        float v = __ldg(Mat + (rb + q) * ldm + n);
+        if (WEIGHTED) {
+          float4 w = wsm[q];
+          acc[0] = fmaf(w.x, v, acc[0]);
+          acc[1] = fmaf(w.y, v, acc[1]);
+          acc[2] = fmaf(w.z, v, acc[2]);
+          acc[NE - 1] = fmaf(w.w, v, acc[NE - 1]);
+        } else {
+          acc[0] += v;
+        }
+      }
+    }
+  }
+  if (n < N) {
+#pragma unroll
+    for (int e = 0; e < NE; ++e) part[((int64_t)blockIdx.y * NE + e) * N + n] = acc[e];
+  }
+}
+
+// u[r][m] = S[r,:] . W[m,:] (+ b[m] on value rows); one warp per row
+__global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ S, int64_t lds, const float* __restrict__ W,
+                                                     const float* __restrict__ b, float* __restrict__ U, int64_t M, int Hp,
+                                                     int o, int C) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < M; r += nwarps) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = lane; j < Hp; j += 32) {
+      float s = __ldg(S + r * lds + j);
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+        if (m < o) acc[m] = fmaf(s, __ldg(W + m * Hp + j), acc[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], off);
+    if (lane == 0) {
+      const bool vrow = (r % C) == 0;
+      float4 out;
+      out.x = acc[0] + ((vrow && 0 < o) ? __ldg(b + 0) : 0.f);
+      out.y = (1 < o) ? acc[1] + (vrow ? __ldg(b + 1) : 0.f) : 0.f;
+      out.z = (2 < o) ? acc[2] + (vrow ? __ldg(b + 2) : 0.f) : 0.f;
+      out.w = (3 < o) ? acc[3] + (vrow ? __ldg(b + 3) : 0.f) : 0.f;
+      *reinterpret_cast<float4*>(U + r * 4) = out;
+    }
+  }
+}
+
+struct CudaBackend {
+  cudaStream_t st;
+  const char* err;
+  int sms;
+  explicit CudaBackend(void* stream) : st((cudaStream_t)stream), err(nullptr), sms(148) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+      int v = 0;
+      if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+    }
+  }
+  void note(cudaError_t e) { if (e != cudaSuccess && !err) err = cudaGetErrorString(e); }
+  void post() { note(cudaPeekAtLastError()); }
+
+  template <class F>
+  void ew(const F& f, int64_t n) {
+    if (n <= 0) return;
+    int64_t blocks = (n + EW_THREADS - 1) / EW_THREADS;
+    int64_t cap = (int64_t)sms * 32;
+    if (blocks > cap) blocks = cap;
+    ew_kernel<F><<<(unsigned)blocks, EW_THREADS, 0, st>>>(f, n);
+    post();
+  }
+  void gemm_nn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M, int N, int K,
+               bool acc) {
+    if (M <= 0) return;
+    const int BN = (N % 128 == 0) ? 128 : (N % 64 == 0) ? 64 : 32;
+    dim3 grid(N / BN, (unsigned)((M + GEMM_BM - 1) / GEMM_BM));
+#define DGMK_NN(bn)                                                                                   \
+  if (acc) gemm_nn_kernel<bn, true><<<grid, GEMM_NT, 0, st>>>(A, lda, B, ldb, C, ldc, M, K);          \
+  else gemm_nn_kernel<bn, false><<<grid, GEMM_NT, 0, st>>>(A, lda, B, ldb, C, ldc, M, K);
+    if (BN == 128) { DGMK_NN(128) } else if (BN == 64) { DGMK_NN(64) } else { DGMK_NN(32) }
+#undef DGMK_NN
+    post();
+  }
+  void reduce(const float* part, int nparts, int64_t n, float* out) {
+    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, nparts, n, out);
+    post();
+  }
+  void gemm_tn_acc(const float* A, int64_t lda, const float* S, int64_t lds, float* out, int N, int Kd, int64_t M,
+                   float* part, int64_t part_n) {
+    if (M <= 0) return;
+    const int64_t tile = (int64_t)N * Kd;
+    int64_t max_splits = part_n / tile;
+    if (max_splits > 256) max_splits = 256;
+    if (max_splits < 1) { if (!err) err = "internal: partial buffer too small"; return; }
+    // aim for >= 4 waves of CTAs, at least 1024 rows per split, at most max_splits
+    const int BN = (Kd % 128 == 0) ? 128 : (Kd % 64 == 0) ? 64 : 32;
+    const int tiles = (Kd / BN) * ((N + GEMM_BM - 1) / GEMM_BM);
+    int64_t want = ((int64_t)sms * 2 * 4 + tiles - 1) / tiles;
+    int64_t by_rows = (M + 1023) / 1024;
+    int64_t splits = want < by_rows ? want : by_rows;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    int64_t rps = ((M + splits - 1) / splits + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
+    splits = (M + rps - 1) / rps;
+    dim3 grid(Kd / BN, (N + GEMM_BM - 1) / GEMM_BM, (unsigned)splits);
+    if (BN == 128) gemm_tn_kernel<128><<<grid, GEMM_NT, 0, st>>>(A, lda, S, lds, part, N, Kd, M, rps);
+    else if (BN == 64) gemm_tn_kernel<64><<<grid, GEMM_NT, 0, st>>>(A, lda, S, lds, part, N, Kd, M, rps);
+    else gemm_tn_kernel<32><<<grid, GEMM_NT, 0, st>>>(A, lda, S, lds, part, N, Kd, M, rps);
+    post();
+    reduce(part, (int)splits, tile, out);
+  }
+  void wcolsum_acc(const float* Mat, int64_t ldm, int N, const float* Wt, int64_t M, float* out, float* part,
+                   int64_t part_n) {
+    if (M <= 0) return;
+    const int NE = Wt ? 4 : 1;
+    int64_t max_blk = part_n / ((int64_t)NE * N);
+    if (max_blk > 512) max_blk = 512;
+    if (max_blk < 1) { if (!err) err = "internal: partial buffer too small"; return; }
+    const int ctiles = (N + 127) / 128;
+    int64_t want = ((int64_t)sms * 8 + ctiles - 1) / ctiles;
+    int64_t by_rows = (M + 255) / 256;
+    int64_t nblk = want < by_rows ? want : by_rows;
+    if (nblk > max_blk) nblk = max_blk;
+    if (nblk < 1) nblk = 1;
+    int64_t rpb = (M + nblk - 1) / nblk;
+    nblk = (M + rpb - 1) / rpb;
+    dim3 grid(ctiles, (unsigned)nblk);
+    if (Wt) wcolsum_kernel<true><<<grid, 128, 0, st>>>(Mat, ldm, N, Wt, M, rpb, part);
+    else wcolsum_kernel<false><<<grid, 128, 0, st>>>(Mat, ldm, N, Wt, M, rpb, part);
+    post();
+    reduce(part, (int)nblk, (int64_t)NE * N, out);
+  }
+  void rowdot(const float* S, int64_t lds, const float* W, const float* b, float* U, int64_t M, int Hp, int o, int C) {
+    if (M <= 0) return;
+    int64_t blocks = (M + 7) / 8;
+    int64_t cap = (int64_t)sms * 16;
+    if (blocks > cap) blocks = cap;
+    rowdot_kernel<<<(unsigned)blocks, 256, 0, st>>>(S, lds, W, b, U, M, Hp, o, C);
+    post();
+  }
+  void zero(void* p, size_t bytes) { note(cudaMemsetAsync(p, 0, bytes, st)); }
+  void copy(void* dst, const void* src, size_t bytes) { note(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st)); }
+  bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+  }
+  const char* error() { post(); return err; }
+};
+
+}  // namespace dgmk
+
+DGMK_DEFINE_C_API(dgmk::CudaBackend, "cuda-sm100a")

@@ -1,0 +1,469 @@
+// Element-wise stages of the jet pipeline, written as POD functors over a flat
+// index so that the CUDA backend can launch them as kernels and the test-only
+// host harness can loop over them.  One functor call handles one
+// (collocation point, hidden unit) pair and owns ALL channels of that pair.
+//
+// Activations live in HBM as [rows*C, ld] row-major FP32, GEMM row = point*C + c.
+// Gate outputs are stored in "a-form": channel 0 holds the OUTPUT value y,
+// channels >=1 hold the PRE-activation tangents (what the adjoint needs:
+// sigma'' and sigma''' terms multiply a_x, a_xx).
+#pragma once
+#include "dgmk_layout.h"
+#include "dgmk_math.h"
+
+namespace dgmk {
+
+struct F4 { float x, y, z, w; };
+
+// Where the coordinates of row r of a pass come from: up to 3 separate arrays
+// (heat companions X0 | XBD1 | XBD2) or one array walked in blocks with a stride
+// (Fredholm nodes T[k, B]: block j = j-th Monte-Carlo draw).
+struct XSrc {
+  const float* p[3];
+  int64_t block_rows;    // rows per block
+  int64_t block_stride;  // floats between consecutive blocks when nptr == 1
+  int32_t nptr, d;
+  DGMK_HD const float* at(int64_t r) const {
+    int64_t b = r / block_rows, w = r - b * block_rows;
+    // ternaries, not p[b]: a runtime index would spill the parameter array to local memory
+    const float* base = (nptr > 1) ? (b == 0 ? p[0] : (b == 1 ? p[1] : p[2])) : p[0] + b * block_stride;
+    return base + w * d;
+  }
+};
+
+// ---- parameter packing --------------------------------------------------------
+struct PackFn {
+  SegTable t; const float* theta; float* packed;
+  DGMK_HD void operator()(int64_t i) const {
+    for (int s = 0; s < t.n; ++s) {
+      const Seg& g = t.s[s];
+      int32_t k = (int32_t)i - g.theta_off;
+      if (k >= 0 && k < g.n) {
+        int r = k / g.cols, c = k - r * g.cols;
+        float v = theta[i];
+        if (g.a_off >= 0) packed[g.a_off + (int64_t)r * g.a_rs + (int64_t)c * g.a_cs] = v;
+        if (g.b_off >= 0) packed[g.b_off + (int64_t)r * g.b_rs + (int64_t)c * g.b_cs] = v;
+        return;
+      }
+    }
+  }
+};
+// grad_theta[i] = packed_grad[...] (dead parameters: 0)
+struct UnpackGradFn {
+  SegTable t; const float* gp; float* grad;
+  DGMK_HD void operator()(int64_t i) const {
+    for (int s = 0; s < t.n; ++s) {
+      const Seg& g = t.s[s];
+      int32_t k = (int32_t)i - g.theta_off;
+      if (k >= 0 && k < g.n) {
+        int r = k / g.cols, c = k - r * g.cols;
+        grad[i] = (g.a_off >= 0) ? gp[g.a_off + (int64_t)r * g.a_rs + (int64_t)c * g.a_cs] : 0.f;
+        return;
+      }
+    }
+  }
+};
+
+// ---- E: extended inputs, [rows*C][4] = (x0|e0, x1|e1, 1|0, 0) -----------------
+// grad[U | b] = Abar^T E  (SURVEY 7.1 "input map").
+template <class CS>
+struct ExtInputFn {
+  XSrc xs; float* E;
+  DGMK_HD void operator()(int64_t p) const {
+    const float* x = xs.at(p);
+    float* e = E + p * CS::C * 4;
+    e[0] = x[0]; e[1] = (xs.d > 1) ? x[1] : 0.f; e[2] = 1.f; e[3] = 0.f;
+#pragma unroll
+    for (int c = 1; c < CS::C; ++c) {
+      float* ec = e + c * 4;
+      ec[0] = (c == 1) ? 1.f : 0.f;
+      ec[1] = (c == 2 && CS::ND > 1) ? 1.f : 0.f;
+      ec[2] = 0.f; ec[3] = 0.f;
+    }
+  }
+};
+
+// ---- input layer: s0 = act(W_in x + b) (dgm_net.py:112, neural_networks.py:241,172)
+template <class CS, int ACT>
+struct InputFwdFn {
+  XSrc xs; const F4* inb; float* S0; int Hp;
+  DGMK_HD void operator()(int64_t i) const {
+    int64_t p = i / Hp; int j = (int)(i - p * Hp);
+    const float* x = xs.at(p);
+    F4 w = inb[j];
+    float a[CS::C], y[CS::C];
+    a[0] = w.x * x[0] + w.z;
+    if (xs.d > 1) a[0] += w.y * x[1];
+#pragma unroll
+    for (int k = 0; k < CS::ND; ++k) a[1 + k] = (k == 0) ? w.x : w.y;
+#pragma unroll
+    for (int q = 0; q < CS::NP; ++q) a[1 + CS::ND + q] = 0.f;
+    act_fwd<CS, ACT>(a, y);
+    float* o = S0 + (p * CS::C) * Hp + j;
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) o[(int64_t)c * Hp] = y[c];
+  }
+};
+template <class CS, int ACT>
+struct InputRevFn {
+  const F4* inb; const float* S0; const float* SB; float* AB; int Hp; int64_t ldab;
+  DGMK_HD void operator()(int64_t i) const {
+    int64_t p = i / Hp; int j = (int)(i - p * Hp);
+    F4 w = inb[j];
+    float af[CS::C], yb[CS::C], ab[CS::C];
+    af[0] = S0[(p * CS::C) * Hp + j];
+#pragma unroll
+    for (int k = 0; k < CS::ND; ++k) af[1 + k] = (k == 0) ? w.x : w.y;
+#pragma unroll
+    for (int q = 0; q < CS::NP; ++q) af[1 + CS::ND + q] = 0.f;
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) yb[c] = SB[(p * CS::C + c) * Hp + j];
+    act_adj<CS, ACT>(yb, af, ab);
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) AB[(p * CS::C + c) * ldab + j] = ab[c];
+  }
+};
+
+// ---- MLP hidden layer: y = act(W y_prev + b) (neural_networks.py:242-243) ------
+template <class CS, int ACT>
+struct MlpActFn {
+  float* G; const F4* ub; float* Yn; int Hp;  // G: GEMM output -> a-form in place
+  DGMK_HD void operator()(int64_t i) const {
+    int64_t p = i / Hp; int j = (int)(i - p * Hp);
+    float a[CS::C], y[CS::C];
+    float* g = G + (p * CS::C) * Hp + j;
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) a[c] = g[(int64_t)c * Hp];
+    a[0] += ub[j].z;
+    act_fwd<CS, ACT>(a, y);
+    g[0] = y[0];
+    float* o = Yn + (p * CS::C) * Hp + j;
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) o[(int64_t)c * Hp] = y[c];
+  }
+};
+template <class CS, int ACT>
+struct MlpRevFn {
+  const float* G; const float* YB; float* AB; int Hp;
+  DGMK_HD void operator()(int64_t i) const {
+    int64_t p = i / Hp; int j = (int)(i - p * Hp);
+    float af[CS::C], yb[CS::C], ab[CS::C];
+    int64_t base = (p * CS::C) * Hp + j;
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) { af[c] = G[base + (int64_t)c * Hp]; yb[c] = YB[base + (int64_t)c * Hp]; }
+    act_adj<CS, ACT>(yb, af, ab);
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) AB[base + (int64_t)c * Hp] = ab[c];
+  }
+};
+
+// ---- DGM layer (dgm_net.py:63-67; neural_networks.py:115-126) -------------------
+// gate slots in the [rows*C, 4Hp] a-form buffer: 0=Z 1=G 2=R 3=H
+template <class CS>
+DGMK_HD void add_input_map(float* a, const F4& u, const float* x, int d) {
+  a[0] += u.x * x[0] + u.z;
+  if (d > 1) a[0] += u.y * x[1];
+#pragma unroll
+  for (int k = 0; k < CS::ND; ++k) a[1 + k] += (k == 0) ? u.x : u.y;
+}
+// stage 1: Z, G, R = act(W s + U x + b) in place (a-form), SR = s * R
+template <class CS, int ACT>
+struct DgmFwd1Fn {
+  XSrc xs; float* A4; const F4* ub; const float* S; float* SR; int Hp;
+  DGMK_HD void operator()(int64_t i) const {
+    int64_t p = i / Hp; int j = (int)(i - p * Hp);
+    const float* x = xs.at(p);
+    const int64_t ld = 4 * (int64_t)Hp;
+    float a[CS::C], y[CS::C];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      float* ag = A4 + (p * CS::C) * ld + g * Hp + j;
+#pragma unroll
+      for (int c = 0; c < CS::C; ++c) a[c] = ag[c * ld];
+      add_input_map<CS>(a, ub[g * Hp + j], x, xs.d);
+      act_fwd<CS, ACT>(a, y);
+      ag[0] = y[0];
+#pragma unroll
+      for (int k = 0; k < CS::ND; ++k) ag[(1 + k) * ld] = a[1 + k];
+    }
+    // y now holds the R jet
+    float s[CS::C], r[CS::C];
+    int64_t sb = (p * CS::C) * Hp + j;
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) s[c] = S[sb + (int64_t)c * Hp];
+    prod_fwd<CS>(s, y, r);
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) SR[sb + (int64_t)c * Hp] = r[c];
+  }
+};
+// stage 2: H = act(W (s*R) + U x + b) in place; s' = (1-G)*H + Z*s
+template <class CS, int ACT>
+struct DgmFwd2Fn {
+  XSrc xs; float* A4; const F4* ub; const float* S; float* Sn; int Hp;
+  DGMK_HD void operator()(int64_t i) const {
+    int64_t p = i / Hp; int j = (int)(i - p * Hp);
+    const float* x = xs.at(p);
+    const int64_t ld = 4 * (int64_t)Hp;
+    float a[CS::C], h[CS::C], z[CS::C], g[CS::C], s[CS::C], t1[CS::C], t2[CS::C];
+    float* row = A4 + (p * CS::C) * ld + j;
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) a[c] = row[c * ld + 3 * Hp];
+    add_input_map<CS>(a, ub[3 * Hp + j], x, xs.d);
+    act_fwd<CS, ACT>(a, h);
+    row[3 * Hp] = h[0];
+#pragma unroll
+    for (int k = 0; k < CS::ND; ++k) row[(1 + k) * ld + 3 * Hp] = a[1 + k];
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) { t1[c] = row[c * ld]; t2[c] = row[c * ld + Hp]; }
+    aform_to_jet<CS, ACT>(t1, z);
+    aform_to_jet<CS, ACT>(t2, g);
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) g[c] = -g[c];
+    g[0] += 1.0f;  // 1 - G
+    int64_t sb = (p * CS::C) * Hp + j;
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) s[c] = S[sb + (int64_t)c * Hp];
+    prod_fwd<CS>(g, h, t1);
+    prod_fwd<CS>(z, s, t2);
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) Sn[sb + (int64_t)c * Hp] = t1[c] + t2[c];
+  }
+};
+// reverse stage 1: from s'bar -> abar_H (slot 3), abar_Z (0), abar_G (1), direct s bar
+template <class CS, int ACT>
+struct DgmRev1Fn {
+  const float* A4; const float* S; const float* SBn; float* AB4; float* SBp; int Hp;
+  DGMK_HD void operator()(int64_t i) const {
+    int64_t p = i / Hp; int j = (int)(i - p * Hp);
+    const int64_t ld = 4 * (int64_t)Hp;
+    const float* row = A4 + (p * CS::C) * ld + j;
+    float* orow = AB4 + (p * CS::C) * ld + j;
+    int64_t sb = (p * CS::C) * Hp + j;
+    float afz[CS::C], afg[CS::C], afh[CS::C], z[CS::C], omg[CS::C], h[CS::C], s[CS::C], nb[CS::C];
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) {
+      afz[c] = row[c * ld]; afg[c] = row[c * ld + Hp]; afh[c] = row[c * ld + 3 * Hp];
+      s[c] = S[sb + (int64_t)c * Hp]; nb[c] = SBn[sb + (int64_t)c * Hp];
+    }
+    aform_to_jet<CS, ACT>(afz, z);
+    aform_to_jet<CS, ACT>(afg, omg);
+    aform_to_jet<CS, ACT>(afh, h);
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) omg[c] = -omg[c];
+    omg[0] += 1.0f;
+    float yb[CS::C], ab[CS::C];
+    prod_adj<CS, false>(nb, omg, yb);  // Hbar
+    act_adj<CS, ACT>(yb, afh, ab);
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) orow[c * ld + 3 * Hp] = ab[c];
+    prod_adj<CS, false>(nb, h, yb);    // -(Gbar)
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) yb[c] = -yb[c];
+    act_adj<CS, ACT>(yb, afg, ab);
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) orow[c * ld + Hp] = ab[c];
+    prod_adj<CS, false>(nb, s, yb);    // Zbar
+    act_adj<CS, ACT>(yb, afz, ab);
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) orow[c * ld] = ab[c];
+    prod_adj<CS, false>(nb, z, yb);    // direct path to s
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) SBp[sb + (int64_t)c * Hp] = yb[c];
+  }
+};
+// reverse stage 2: (s*R)bar -> abar_R (slot 2), s bar += R * (sR)bar
+template <class CS, int ACT>
+struct DgmRev2Fn {
+  const float* A4; const float* S; const float* SRB; float* AB4; float* SBp; int Hp;
+  DGMK_HD void operator()(int64_t i) const {
+    int64_t p = i / Hp; int j = (int)(i - p * Hp);
+    const int64_t ld = 4 * (int64_t)Hp;
+    const float* row = A4 + (p * CS::C) * ld + 2 * Hp + j;
+    float* orow = AB4 + (p * CS::C) * ld + 2 * Hp + j;
+    int64_t sb = (p * CS::C) * Hp + j;
+    float afr[CS::C], r[CS::C], s[CS::C], srb[CS::C], sbar[CS::C], yb[CS::C], ab[CS::C];
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) {
+      afr[c] = row[c * ld]; s[c] = S[sb + (int64_t)c * Hp];
+      srb[c] = SRB[sb + (int64_t)c * Hp]; sbar[c] = SBp[sb + (int64_t)c * Hp];
+    }
+    aform_to_jet<CS, ACT>(afr, r);
+    prod_adj<CS, false>(srb, s, yb);  // Rbar
+    act_adj<CS, ACT>(yb, afr, ab);
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) orow[c * ld] = ab[c];
+    prod_adj<CS, true>(srb, r, sbar);
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) SBp[sb + (int64_t)c * Hp] = sbar[c];
+  }
+};
+
+// ---- output layer reverse: s bar[r][j] = sum_m ubar[r][m] W_out[m][j] -----------
+struct OutRevFn {
+  const float* UB; const float* outw; float* SB; int Hp; int o;
+  DGMK_HD void operator()(int64_t i) const {
+    int64_t r = i / Hp; int j = (int)(i - r * Hp);
+    float v = 0.f;
+    for (int m = 0; m < o; ++m) v += UB[r * 4 + m] * outw[m * Hp + j];
+    SB[i] = v;
+  }
+};
+
+// ================================ losses =========================================
+// U / UB are [rows*C][4]: output jets (column m = output component) and their
+// cotangent seeds.  Lp[p] is the point's (already scaled) loss contribution.
+
+// heat interior (heat.py:71-87): r = u_t - kappa u_xx
+struct HeatInteriorFn {
+  const float* U; float* UB; float* Lp; float kappa, inv;
+  DGMK_HD void operator()(int64_t p) const {
+    const float* u = U + p * 16;
+    float r = u[8] - kappa * u[12];
+    float* ub = UB + p * 16;
+    for (int q = 0; q < 16; ++q) ub[q] = 0.f;
+    ub[8] = 2.f * r * inv;
+    ub[12] = -2.f * kappa * r * inv;
+    Lp[p] = r * r * inv;
+  }
+};
+// value rows with targets (heat.py:89-94 IC/BC; simple_ode.py:62; fitzhugh_nagumo.py:95)
+// per block b of the pass: mode 0 = target array tgt[b][row*o + m], 1 = sin(x[row][0])
+struct ValueTargetFn {
+  const float* U; float* UB; float* Lp; XSrc xs; const float* tgt[3]; int32_t mode[3];
+  int32_t o; float inv;
+  DGMK_HD void operator()(int64_t p) const {
+    int64_t b = p / xs.block_rows, w = p - b * xs.block_rows;
+    float l = 0.f;
+    for (int m = 0; m < 4; ++m) {
+      float ubv = 0.f;
+      if (m < o) {
+        const int md = b == 0 ? mode[0] : (b == 1 ? mode[1] : mode[2]);
+        const float* tg = b == 0 ? tgt[0] : (b == 1 ? tgt[1] : tgt[2]);
+        float t = (md == 1) ? sinf(xs.at(p)[0]) : tg[w * o + m];
+        float e = U[p * 4 + m] - t;
+        l += e * e;
+        ubv = 2.f * e * inv;
+      }
+      UB[p * 4 + m] = ubv;
+    }
+    Lp[p] = l * inv;
+  }
+};
+// simple ODE interior (simple_ode.py:54-60): r = y_t + y
+struct OdeInteriorFn {
+  const float* U; float* UB; float* Lp; float inv;
+  DGMK_HD void operator()(int64_t p) const {
+    const float* u = U + p * 8;
+    float r = u[4] + u[0];
+    float* ub = UB + p * 8;
+    for (int q = 0; q < 8; ++q) ub[q] = 0.f;
+    ub[0] = 2.f * r * inv;
+    ub[4] = 2.f * r * inv;
+    Lp[p] = r * r * inv;
+  }
+};
+// FitzHugh-Nagumo interior (fitzhugh_nagumo.py:69-94)
+struct FhnInteriorFn {
+  const float* U; float* UB; float* Lp; float I, alpha, beta, tau, inv;
+  DGMK_HD void operator()(int64_t p) const {
+    const float* u = U + p * 8;
+    float Y = u[0], W = u[1], dY = u[4], dW = u[5];
+    float rx = dY + (Y * Y * Y / 3.0f + W - I - Y);
+    float ry = dW + (beta * W - alpha - Y) / tau;
+    float* ub = UB + p * 8;
+    for (int q = 0; q < 8; ++q) ub[q] = 0.f;
+    float gx = 2.f * rx * inv, gy = 2.f * ry * inv;
+    ub[4] = gx;
+    ub[5] = gy;
+    ub[0] = gx * (Y * Y - 1.f) - gy / tau;
+    ub[1] = gx + gy * beta / tau;
+    Lp[p] = (rx * rx + ry * ry) * inv;
+  }
+};
+// Fredholm (fredholm.py:64-74): value rows of the chunk's points (Ux) and of their
+// k Monte-Carlo nodes (Un, row = j*rows + p); accumulation order j = 0..k-1 as in
+// the reference loop.
+struct FredholmFn {
+  const float* Ux; const float* Un; float* UBx; float* UBn; float* Lp;
+  const float* x; const float* T; int64_t rows, Tstride; int32_t k; float dr, inv;
+  DGMK_HD void operator()(int64_t p) const {
+    float sx = sinf(x[p]);
+    float integral = 0.f;
+    for (int j = 0; j < k; ++j) {
+      float w = sx * cosf(T[(int64_t)j * Tstride + p]);
+      integral += w * Un[((int64_t)j * rows + p) * 4];
+    }
+    integral *= dr;
+    float r = Ux[p * 4] - sx - integral;
+    float g = 2.f * r * inv;
+    UBx[p * 4] = g; UBx[p * 4 + 1] = 0.f; UBx[p * 4 + 2] = 0.f; UBx[p * 4 + 3] = 0.f;
+    for (int j = 0; j < k; ++j) {
+      float w = sx * cosf(T[(int64_t)j * Tstride + p]);
+      float* ub = UBn + ((int64_t)j * rows + p) * 4;
+      ub[0] = -g * dr * w; ub[1] = 0.f; ub[2] = 0.f; ub[3] = 0.f;
+    }
+    Lp[p] = r * r * inv;
+  }
+};
+
+// ---- generic jet I/O for the module-level autograd seam -----------
+// U -> Y[B,o], J[B,o,d], Hs[B,o,d,d]
+template <class CS>
+struct JetOutFn {
+  const float* U; float* Y; float* J; float* Hs; int32_t o, d;
+  DGMK_HD void operator()(int64_t p) const {
+    const float* u = U + p * CS::C * 4;
+    for (int m = 0; m < o; ++m) {
+      Y[p * o + m] = u[m];
+      if (J) for (int k = 0; k < CS::ND; ++k) J[(p * o + m) * d + k] = u[(1 + k) * 4 + m];
+      if (Hs) {
+#pragma unroll
+        for (int q = 0; q < CS::NP; ++q) {
+          float v = u[(1 + CS::ND + q) * 4 + m];
+          Hs[((p * o + m) * d + CS::pi(q)) * d + CS::pj(q)] = v;
+          Hs[((p * o + m) * d + CS::pj(q)) * d + CS::pi(q)] = v;
+        }
+      }
+    }
+  }
+};
+// cotangents (gY, gJ, gHs; any may be null) -> UB seeds
+template <class CS>
+struct JetSeedFn {
+  float* UB; const float* gY; const float* gJ; const float* gHs; int32_t o, d;
+  DGMK_HD void operator()(int64_t p) const {
+    float* ub = UB + p * CS::C * 4;
+    for (int m = 0; m < 4; ++m) {
+      bool live = m < o;
+      ub[m] = (live && gY) ? gY[p * o + m] : 0.f;
+#pragma unroll
+      for (int k = 0; k < CS::ND; ++k) ub[(1 + k) * 4 + m] = (live && gJ) ? gJ[(p * o + m) * d + k] : 0.f;
+#pragma unroll
+      for (int q = 0; q < CS::NP; ++q) {
+        float v = 0.f;
+        if (live && gHs) {
+          v = gHs[((p * o + m) * d + CS::pi(q)) * d + CS::pj(q)];
+          if (CS::pi(q) != CS::pj(q)) v += gHs[((p * o + m) * d + CS::pj(q)) * d + CS::pi(q)];
+        }
+        ub[(1 + CS::ND + q) * 4 + m] = v;
+      }
+    }
+  }
+};
+
+// ---- fused Adam on the flat buffers (torch.optim.Adam defaults, heat.py:115) -----
+struct AdamFn {
+  float* theta; float* m; float* v; const float* g; const uint8_t* live;
+  float step_size, bc2_sqrt, w1, b2, w2, eps;  // lr/(1-b1^t), sqrt(1-b2^t), 1-b1, b2, 1-b2
+  DGMK_HD void operator()(int64_t i) const {
+    if (live && !live[i]) return;  // grad is None -> torch skips the parameter
+    float gi = g[i];
+    float mi = m[i] + w1 * (gi - m[i]);      // exp_avg.lerp_(grad, 1 - beta1)
+    float vi = b2 * v[i] + (w2 * gi) * gi;   // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    m[i] = mi; v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    theta[i] -= step_size * (mi / denom);    // param.addcdiv_(exp_avg, denom, value=-step_size)
+  }
+};
+
+}  // namespace dgmk

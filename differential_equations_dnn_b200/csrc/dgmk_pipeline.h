@@ -1,0 +1,261 @@
+// Layer-wise jet pipeline: forward pass (value + input-derivative channels through
+// every layer, a-form stash in HBM), reverse pass (adjoint of the jet program),
+// weight-gradient contractions, and the four fused training steps.
+//
+// Templated on a backend that provides the heavy primitives (GEMM tiles, element-
+// wise launches, reductions).  The product backend is CUDA (dgmk_cuda.cu); the
+// test-only host harness (tests/host_emul) instantiates the same orchestration with
+// plain loops so that buffer offsets, ordering and scaling can be validated against
+// the oracle without a GPU.  There is no CPU path in the shipped library.
+//
+// Reference path replaced: heat.py:50-95 + :136-141, simple_ode.py:41-63 + :96-104,
+// fitzhugh_nagumo.py:53-97 + :135-143, fredholm.py:47-74 + :104-109.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+#include "dgmk_layout.h"
+#include "dgmk_math.h"
+#include "dgmk_ops.h"
+
+namespace dgmk {
+
+// ---- workspace carving ----------------------------------------------------------
+struct Carver {
+  char* base; size_t off, cap; bool ok;
+  Carver(void* b, size_t c) : base((char*)b), off(0), cap(c), ok(true) {}
+  float* take(int64_t nfloats) {
+    size_t bytes = ((size_t)nfloats * 4 + 255) / 256 * 256;
+    if (off + bytes > cap) { ok = false; return nullptr; }
+    float* p = (float*)(base + off);
+    off += bytes;
+    return p;
+  }
+};
+inline size_t carve_bytes(int64_t nfloats) { return ((size_t)nfloats * 4 + 255) / 256 * 256; }
+
+// Buffers of one pass (one set of rows with one channel set)
+struct PassBufs {
+  XSrc xs; int64_t rows; int cs, C; int64_t M;
+  float* E;            // [M][4]
+  float* S[MAX_L + 1]; // layer states / MLP activations, [M][Hp]
+  float* G[MAX_L];     // a-form gates [M][NG*Hp]
+  float* SR[MAX_L];    // DGM: s*R [M][Hp]
+  float* U;            // [M][4] output jets
+  float* UB;           // [M][4] output cotangents
+};
+inline int64_t pass_floats_per_row(const NetDims& n, int C) {
+  // E + states + gates + SR + U + UB (each carved separately; rounding slack added by caller)
+  int64_t Hp = n.Hp;
+  int64_t f = 4 + (n.L + 1) * Hp + n.L * n.NG * Hp + (n.is_dgm() ? n.L * Hp : 0) + 4 + 4;
+  return f * C;
+}
+// reverse scratch, shared by all passes of a step (sized for the largest M)
+struct RevBufs { float* SBa; float* SBb; float* AB; float* SRB; };
+inline int64_t rev_floats_per_row(const NetDims& n, int C) {
+  int64_t Hp = n.Hp;
+  return (2 * Hp + n.NG * Hp + (n.is_dgm() ? Hp : 0)) * C;
+}
+constexpr int64_t PART_FLOATS_MIN = 1 << 20;
+inline int64_t part_floats(const NetDims& n) {
+  // gemm_tn partials: <= 256 splits x [3Hp, Hp]; wcolsum partials: <= 512 blocks x 4 x 4Hp
+  int64_t a = 256LL * 3 * n.Hp * n.Hp, b = 512LL * 4 * 4 * n.Hp;
+  int64_t m = a > b ? a : b;
+  return m > PART_FLOATS_MIN ? m : PART_FLOATS_MIN;
+}
+
+struct Ctx {
+  NetDims n; PackedLayout pl; SegTable pack, grad;
+  float* Wp;    // packed weights
+  float* Gp;    // packed gradient accumulators (Gp[pl.g_acc] = loss)
+  float* part;  // reduction partials
+  int64_t part_n;
+  float* Lp;    // per-point loss contributions
+};
+
+inline bool carve_pass(Carver& cv, const NetDims& n, PassBufs* pb, int64_t rows, int cs) {
+  pb->rows = rows; pb->cs = cs; pb->C = cs_channels(cs); pb->M = rows * pb->C;
+  const int64_t M = pb->M, Hp = n.Hp;
+  pb->E = cv.take(M * 4);
+  for (int l = 0; l <= n.L; ++l) pb->S[l] = cv.take(M * Hp);
+  for (int l = 0; l < n.L; ++l) {
+    pb->G[l] = cv.take(M * n.NG * Hp);
+    pb->SR[l] = n.is_dgm() ? cv.take(M * Hp) : nullptr;
+  }
+  pb->U = cv.take(M * 4);
+  pb->UB = cv.take(M * 4);
+  return cv.ok;
+}
+inline size_t pass_bytes(const NetDims& n, int64_t rows, int cs) {
+  int64_t C = cs_channels(cs), M = rows * C, Hp = n.Hp;
+  size_t b = carve_bytes(M * 4) * 3 + carve_bytes(M * Hp) * (n.L + 1) + carve_bytes(M * n.NG * Hp) * n.L;
+  if (n.is_dgm()) b += carve_bytes(M * Hp) * n.L;
+  return b;
+}
+inline bool carve_rev(Carver& cv, const NetDims& n, RevBufs* rb, int64_t Mmax) {
+  rb->SBa = cv.take(Mmax * n.Hp);
+  rb->SBb = cv.take(Mmax * n.Hp);
+  rb->AB = cv.take(Mmax * n.NG * n.Hp);
+  rb->SRB = n.is_dgm() ? cv.take(Mmax * n.Hp) : nullptr;
+  return cv.ok;
+}
+inline size_t rev_bytes(const NetDims& n, int64_t Mmax) {
+  size_t b = carve_bytes(Mmax * n.Hp) * 2 + carve_bytes(Mmax * n.NG * n.Hp);
+  if (n.is_dgm()) b += carve_bytes(Mmax * n.Hp);
+  return b;
+}
+inline bool carve_ctx(Carver& cv, Ctx* c, int64_t max_points) {
+  c->Wp = cv.take(c->pl.w_total);
+  c->Gp = cv.take(c->pl.g_total);
+  c->part_n = part_floats(c->n);
+  c->part = cv.take(c->part_n);
+  c->Lp = cv.take(max_points);
+  return cv.ok;
+}
+inline size_t ctx_bytes(const NetDims& n, const PackedLayout& pl, int64_t max_points) {
+  return carve_bytes(pl.w_total) + carve_bytes(pl.g_total) + carve_bytes(part_floats(n)) + carve_bytes(max_points);
+}
+
+// ---- dispatch helpers --------------------------------------------------------------
+#define DGMK_CS_SWITCH(cs, CS, ...)                                  \
+  switch (cs) {                                                      \
+    case CS_V: { using CS = CsV; __VA_ARGS__; } break;               \
+    case CS_D1O1: { using CS = CsD1O1; __VA_ARGS__; } break;         \
+    case CS_HEAT: { using CS = CsHeat; __VA_ARGS__; } break;         \
+    case CS_D2O1: { using CS = CsD2O1; __VA_ARGS__; } break;         \
+    case CS_D1O2: { using CS = CsD1O2; __VA_ARGS__; } break;         \
+    default: { using CS = CsD2O2; __VA_ARGS__; } break;              \
+  }
+#define DGMK_ACT_SWITCH(act, ACT, ...)                                       \
+  switch (act) {                                                             \
+    case ACT_RELU: { constexpr int ACT = ACT_RELU; __VA_ARGS__; } break;     \
+    case ACT_SIGMOID: { constexpr int ACT = ACT_SIGMOID; __VA_ARGS__; } break; \
+    case ACT_TANH: { constexpr int ACT = ACT_TANH; __VA_ARGS__; } break;     \
+    default: { constexpr int ACT = ACT_LEAKY; __VA_ARGS__; } break;          \
+  }
+// DGM stacks only ever use tanh (dgm_net) or relu (neural_networks.DGM)
+#define DGMK_GACT_SWITCH(act, ACT, ...)                                      \
+  if ((act) == ACT_TANH) { constexpr int ACT = ACT_TANH; __VA_ARGS__; }      \
+  else { constexpr int ACT = ACT_RELU; __VA_ARGS__; }
+
+template <class BK>
+struct Pipeline {
+  BK& bk; Ctx& c;
+  Pipeline(BK& b, Ctx& ctx) : bk(b), c(ctx) {}
+
+  const F4* inb() const { return (const F4*)(c.Wp + c.pl.inb); }
+  const F4* ub(int l) const { return (const F4*)(c.Wp + c.pl.ub[l]); }
+
+  void pack(const float* theta) {
+    bk.zero(c.Wp, (size_t)c.pl.w_total * 4);
+    PackFn f; f.t = c.pack; f.theta = theta; f.packed = c.Wp;
+    bk.ew(f, num_params(c.n));
+  }
+  void zero_grads() { bk.zero(c.Gp, (size_t)c.pl.g_total * 4); }
+  void unpack(float* grad_theta, float* loss_out) {
+    UnpackGradFn f; f.t = c.grad; f.gp = c.Gp; f.grad = grad_theta;
+    if (grad_theta) bk.ew(f, num_params(c.n));
+    if (loss_out) bk.copy(loss_out, c.Gp + c.pl.g_acc, 4);
+  }
+
+  // ---------------------------------------------------------------- forward
+  void forward(PassBufs& pb) {
+    const NetDims& n = c.n;
+    const int Hp = n.Hp;
+    const int64_t M = pb.M, R = pb.rows;
+    DGMK_CS_SWITCH(pb.cs, CS, {
+      ExtInputFn<CS> fe; fe.xs = pb.xs; fe.E = pb.E;
+      bk.ew(fe, R);
+      DGMK_ACT_SWITCH(n.in_act(), ACT, {
+        InputFwdFn<CS, ACT> f; f.xs = pb.xs; f.inb = inb(); f.S0 = pb.S[0]; f.Hp = Hp;
+        bk.ew(f, R * Hp);
+      })
+      for (int l = 0; l < n.L; ++l) {
+        if (!n.is_dgm()) {
+          bk.gemm_nn(pb.S[l], Hp, c.Wp + c.pl.wf[l], Hp, pb.G[l], Hp, M, Hp, Hp, false);
+          DGMK_ACT_SWITCH(n.act, ACT, {
+            MlpActFn<CS, ACT> f; f.G = pb.G[l]; f.ub = ub(l); f.Yn = pb.S[l + 1]; f.Hp = Hp;
+            bk.ew(f, R * Hp);
+          })
+        } else {
+          bk.gemm_nn(pb.S[l], Hp, c.Wp + c.pl.wf[l], 3 * Hp, pb.G[l], 4 * Hp, M, 3 * Hp, Hp, false);
+          DGMK_GACT_SWITCH(n.gate_act(), ACT, {
+            DgmFwd1Fn<CS, ACT> f; f.xs = pb.xs; f.A4 = pb.G[l]; f.ub = ub(l); f.S = pb.S[l]; f.SR = pb.SR[l]; f.Hp = Hp;
+            bk.ew(f, R * Hp);
+          })
+          bk.gemm_nn(pb.SR[l], Hp, c.Wp + c.pl.wfh[l], Hp, pb.G[l] + 3 * Hp, 4 * Hp, M, Hp, Hp, false);
+          DGMK_GACT_SWITCH(n.gate_act(), ACT, {
+            DgmFwd2Fn<CS, ACT> f; f.xs = pb.xs; f.A4 = pb.G[l]; f.ub = ub(l); f.S = pb.S[l]; f.Sn = pb.S[l + 1]; f.Hp = Hp;
+            bk.ew(f, R * Hp);
+          })
+        }
+      }
+    })
+    bk.rowdot(pb.S[n.L], Hp, c.Wp + c.pl.outw, c.Wp + c.pl.outb, pb.U, M, Hp, n.o, pb.C);
+  }
+
+  // ---------------------------------------------------------------- reverse
+  // pb.UB holds the output cotangents; gradients are ACCUMULATED into c.Gp.
+  void reverse(PassBufs& pb, RevBufs& rb) {
+    const NetDims& n = c.n;
+    const int Hp = n.Hp;
+    const int64_t M = pb.M, R = pb.rows;
+    float* Gp = c.Gp;
+    // output layer: grad W_out = UB^T S_L, grad b_out = sum of value-row cotangents
+    bk.wcolsum_acc(pb.S[n.L], Hp, Hp, pb.UB, M, Gp + c.pl.g_outw, c.part, c.part_n);
+    bk.wcolsum_acc(pb.UB, 4, 4, pb.E, M, Gp + c.pl.g_outb, c.part, c.part_n);
+    float* SBn = rb.SBa;  // cotangent of the current layer's output
+    float* SBp = rb.SBb;
+    {
+      OutRevFn f; f.UB = pb.UB; f.outw = c.Wp + c.pl.outw; f.SB = SBn; f.Hp = Hp; f.o = n.o;
+      bk.ew(f, M * Hp);
+    }
+    DGMK_CS_SWITCH(pb.cs, CS, {
+      for (int l = n.L - 1; l >= 0; --l) {
+        if (!n.is_dgm()) {
+          DGMK_ACT_SWITCH(n.act, ACT, {
+            MlpRevFn<CS, ACT> f; f.G = pb.G[l]; f.YB = SBn; f.AB = rb.AB; f.Hp = Hp;
+            bk.ew(f, R * Hp);
+          })
+          bk.gemm_tn_acc(rb.AB, Hp, pb.S[l], Hp, Gp + c.pl.g_w[l], Hp, Hp, M, c.part, c.part_n);
+          bk.wcolsum_acc(rb.AB, Hp, Hp, pb.E, M, Gp + c.pl.g_ub[l], c.part, c.part_n);
+          bk.gemm_nn(rb.AB, Hp, c.Wp + c.pl.wb[l], Hp, SBp, Hp, M, Hp, Hp, false);
+        } else {
+          DGMK_GACT_SWITCH(n.gate_act(), ACT, {
+            DgmRev1Fn<CS, ACT> f; f.A4 = pb.G[l]; f.S = pb.S[l]; f.SBn = SBn; f.AB4 = rb.AB; f.SBp = SBp; f.Hp = Hp;
+            bk.ew(f, R * Hp);
+          })
+          // (s*R)bar = abar_H W_h
+          bk.gemm_nn(rb.AB + 3 * Hp, 4 * Hp, c.Wp + c.pl.wb[l] + (int64_t)3 * Hp * Hp, Hp, rb.SRB, Hp, M, Hp, Hp, false);
+          DGMK_GACT_SWITCH(n.gate_act(), ACT, {
+            DgmRev2Fn<CS, ACT> f; f.A4 = pb.G[l]; f.S = pb.S[l]; f.SRB = rb.SRB; f.AB4 = rb.AB; f.SBp = SBp; f.Hp = Hp;
+            bk.ew(f, R * Hp);
+          })
+          // s bar += [abar_Z | abar_G | abar_R] [W_z; W_g; W_r]
+          bk.gemm_nn(rb.AB, 4 * Hp, c.Wp + c.pl.wb[l], Hp, SBp, Hp, M, Hp, 3 * Hp, true);
+          // weight gradients
+          bk.gemm_tn_acc(rb.AB, 4 * Hp, pb.S[l], Hp, Gp + c.pl.g_w[l], 3 * Hp, Hp, M, c.part, c.part_n);
+          bk.gemm_tn_acc(rb.AB + 3 * Hp, 4 * Hp, pb.SR[l], Hp, Gp + c.pl.g_w[l] + (int64_t)3 * Hp * Hp, Hp, Hp, M, c.part, c.part_n);
+          bk.wcolsum_acc(rb.AB, 4 * Hp, 4 * Hp, pb.E, M, Gp + c.pl.g_ub[l], c.part, c.part_n);
+        }
+        float* t = SBn; SBn = SBp; SBp = t;
+      }
+      DGMK_ACT_SWITCH(n.in_act(), ACT, {
+        InputRevFn<CS, ACT> f; f.inb = inb(); f.S0 = pb.S[0]; f.SB = SBn; f.AB = rb.AB; f.Hp = Hp; f.ldab = Hp;
+        bk.ew(f, R * Hp);
+      })
+      bk.wcolsum_acc(rb.AB, Hp, Hp, pb.E, M, Gp + c.pl.g_inb, c.part, c.part_n);
+    })
+  }
+
+  void add_loss(int64_t rows) {
+    bk.wcolsum_acc(c.Lp, 1, 1, nullptr, rows, c.Gp + c.pl.g_acc, c.part, c.part_n);
+  }
+};
+
+inline XSrc xsrc1(const float* p, int64_t rows, int d) {
+  XSrc x; x.p[0] = p; x.p[1] = x.p[2] = nullptr; x.block_rows = rows > 0 ? rows : 1; x.block_stride = 0; x.nptr = 1; x.d = d;
+  return x;
+}
+
+}  // namespace dgmk

@@ -1,0 +1,133 @@
+/* dgmk -- C ABI of the B200-native collocation training step.
+ *
+ * The reference (gdetor/differential_equations_dnn) is pure Python on torch: it
+ * has no FFI layer.  The boundary this library replaces is the pair of Python
+ * seams SURVEY.md 8(b) identifies; each entry point below cites the reference
+ * code whose work it performs.  Callers are the torch.autograd.Functions in
+ * differential_equations_dnn_b200/ (via ctypes); see INTEGRATION.md for the stub
+ * a reference maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to FP32 data owned by the caller, except
+ *    `desc` and where stated; the library allocates nothing and keeps no pointer
+ *    after returning;
+ *  - `theta` / `grad_theta` use the reference modules' named_parameters() order
+ *    (dgmk_param_layout enumerates it);
+ *  - work is enqueued on `stream` (a cudaStream_t passed as void*) and the call
+ *    returns without synchronising; CUDA errors surface on the next call or on
+ *    the caller's synchronise;
+ *  - return value: 0 on success, negative DGMK_E* on failure with a message in
+ *    dgmk_last_error() (thread-local).  Never exits, never throws;
+ *  - re-entrant; concurrent calls on different streams/devices are safe as long
+ *    as their workspaces are distinct.
+ *  - There is no CPU implementation: host pointers are an error (DGMK_EDEVICE).
+ */
+#ifndef DGMK_H
+#define DGMK_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGMK_VERSION 100
+
+enum { DGMK_OK = 0, DGMK_EINVAL = -1, DGMK_EWORKSPACE = -2, DGMK_ECUDA = -3, DGMK_EDEVICE = -4 };
+
+/* network families on the hot path */
+enum {
+  DGMK_MLP = 0,        /* neural_networks.MLP, no batch-norm (neural_networks.py:180-270) */
+  DGMK_DGM_LINEAR = 1, /* dgm_net.DGM (dgm_net.py:71-119)                                 */
+  DGMK_DGM_RAW = 2     /* neural_networks.DGM (neural_networks.py:130-177)                */
+};
+/* neural_networks.selectActivationFunction (neural_networks.py:24-41) */
+enum { DGMK_RELU = 0, DGMK_SIGMOID = 1, DGMK_TANH = 2, DGMK_LEAKY_RELU = 3 };
+
+/* workspace sizing classes */
+enum {
+  DGMK_WS_HEAT = 0, DGMK_WS_ODE = 1, DGMK_WS_FHN = 2, DGMK_WS_FREDHOLM = 3,
+  DGMK_WS_JET0 = 4, DGMK_WS_JET1 = 5, DGMK_WS_JET2 = 6
+};
+
+typedef struct {
+  int32_t kind;        /* DGMK_MLP / DGMK_DGM_LINEAR / DGMK_DGM_RAW          */
+  int32_t input_dim;   /* d: 1 or 2                                          */
+  int32_t output_dim;  /* o: 1..4                                            */
+  int32_t hidden_size; /* H                                                  */
+  int32_t num_layers;  /* L (same meaning as the reference constructors)     */
+  int32_t activation;  /* MLP only; DGM_LINEAR is tanh, DGM_RAW is relu      */
+  int32_t reserved[2];
+} dgmk_net_desc;
+
+int dgmk_version(void);
+const char* dgmk_backend(void);    /* "cuda-sm100a" for the shipped library */
+const char* dgmk_last_error(void);
+
+/* Flat parameter layout = named_parameters() order of the reference module.
+ * dgmk_param_count: total number of floats (includes neural_networks.DGM's dead
+ * `dgm1` sub-layer, neural_networks.py:145).  dgmk_param_layout: tensor `index`
+ * (0-based) -> offset/shape/live; returns the number of tensors when index < 0,
+ * DGMK_EINVAL past the end. */
+int64_t dgmk_param_count(const dgmk_net_desc* desc);
+int dgmk_param_layout(const dgmk_net_desc* desc, int32_t index, int64_t* offset, int32_t* rows,
+                      int32_t* cols, int32_t* live);
+
+/* Recommended workspace size for `B` rows (Fredholm: k nodes per row).  The step
+ * entry points process the batch in chunks sized to whatever workspace they are
+ * given (any size >= dgmk_workspace_bytes(desc, cls, 1024, k) works); the jet
+ * entry points need the full dgmk_workspace_bytes(desc, DGMK_WS_JETn, B, 0) because
+ * the stash must survive from dgmk_jet_forward to dgmk_jet_reverse. */
+size_t dgmk_workspace_bytes(const dgmk_net_desc* desc, int32_t ws_class, int64_t B, int32_t k);
+
+/* ---- fused training steps: loss + d loss / d theta in one call ---------------
+ * Each replaces `dgm_loss_func(...)` + `loss.backward()` of one reference script.
+ * `B` rows are local to this call; every per-row term is scaled by 1/B_global so
+ * that data-parallel ranks can SUM their (loss, grad).  `loss` is one
+ * device float.  grad_theta of parameters the reference leaves at grad=None is 0. */
+
+/* heat.py:50-95 -- x,x0,xbd1,xbd2: [B,2] (col0 = x, col1 = t); x_bd1,x_bd2: [B,1] */
+int dgmk_heat_step(const dgmk_net_desc* desc, const float* theta, const float* x, const float* x0,
+                   const float* xbd1, const float* xbd2, const float* x_bd1, const float* x_bd2,
+                   int64_t B, int64_t B_global, float kappa, float* loss, float* grad_theta,
+                   void* ws, size_t ws_bytes, void* stream);
+/* simple_ode.py:41-63 with y = net(t), y0 = net(t0) (driver :98-101); t,t0,y_ic: [B,1] */
+int dgmk_ode_step(const dgmk_net_desc* desc, const float* theta, const float* t, const float* t0,
+                  const float* y_ic, int64_t B, int64_t B_global, float* loss, float* grad_theta,
+                  void* ws, size_t ws_bytes, void* stream);
+/* fitzhugh_nagumo.py:53-97; t,t0: [B,1], y_ic: [B,2]; net output_dim must be 2 */
+int dgmk_fhn_step(const dgmk_net_desc* desc, const float* theta, const float* t, const float* t0,
+                  const float* y_ic, int64_t B, int64_t B_global, float* loss, float* grad_theta,
+                  void* ws, size_t ws_bytes, void* stream);
+/* fredholm.py:47-74; x: [B,1]; nodes: [k,B,1], nodes[j] = the j-th `pi/2*rand_like(x)` */
+int dgmk_fredholm_step(const dgmk_net_desc* desc, const float* theta, const float* x,
+                       const float* nodes, int64_t B, int32_t k, int64_t B_global, float* loss,
+                       float* grad_theta, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- module-level seam: net(x) with input derivatives --------------------------
+ * Replaces `net(x)` followed by nested torch.autograd.grad(create_graph=True)
+ * (heat.py:71-85).  order 0: Y only; 1: Y,J; 2: Y,J,Hs.  Y [B,o], J [B,o,d],
+ * Hs [B,o,d,d] (symmetric).  dgmk_jet_reverse takes cotangents of all three (NULL =
+ * zero) and ACCUMULATES nothing: grad_theta is overwritten. */
+int dgmk_jet_forward(const dgmk_net_desc* desc, const float* theta, const float* x, int64_t B,
+                     int32_t order, float* Y, float* J, float* Hs, void* ws, size_t ws_bytes,
+                     void* stream);
+int dgmk_jet_reverse(const dgmk_net_desc* desc, const float* theta, const float* x, int64_t B,
+                     int32_t order, const float* gY, const float* gJ, const float* gHs,
+                     float* grad_theta, void* ws, size_t ws_bytes, void* stream);
+/* value-only forward in chunks (gridEvaluation, heat.py:152-172) */
+int dgmk_eval(const dgmk_net_desc* desc, const float* theta, const float* x, int64_t B, float* Y,
+              void* ws, size_t ws_bytes, void* stream);
+
+/* ---- torch.optim.Adam(lr) defaults on the flat buffers (heat.py:115,141) --------
+ * step = 1-based step count AFTER increment; live (uint8, may be NULL) = 0 for
+ * parameters whose grad is None in the reference (skipped entirely).  The
+ * hyper-parameters are doubles because torch forms 1-beta and the bias corrections
+ * in Python doubles before touching FP32 tensors. */
+int dgmk_adam(float* theta, float* m, float* v, const float* grad, const uint8_t* live, int64_t P,
+              double lr, double beta1, double beta2, double eps, int64_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGMK_H */

@@ -1,0 +1,61 @@
+// TEST INFRASTRUCTURE ONLY -- never shipped, never loaded by the package.
+//
+// Instantiates the SAME orchestration templates as the CUDA library
+// (csrc/dgmk_pipeline.h, dgmk_capi_impl.h, dgmk_ops.h) with a backend made of plain
+// host loops, so that tests can check buffer carving, layer ordering, packing and
+// scaling against the oracle in the GPU-less build container.  The GEMM tiles and
+// reduction kernels themselves are CUDA-only and are covered by the -m gpu tests.
+// Built by tests/host_emul/build.sh into tests/host_emul/libdgmk_emul.so.
+#include <vector>
+#include "../../differential_equations_dnn_b200/csrc/dgmk_capi_impl.h"
+
+namespace {
+struct HostBackend {
+  explicit HostBackend(void*) {}
+  template <class F> void ew(const F& f, int64_t n) { for (int64_t i = 0; i < n; ++i) f(i); }
+  void gemm_nn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M, int N, int K, bool acc) {
+    for (int64_t m = 0; m < M; ++m)
+      for (int n = 0; n < N; ++n) {
+        float s = 0.f;
+        for (int k = 0; k < K; ++k) s = fmaf(A[m * lda + k], B[(int64_t)k * ldb + n], s);
+        C[m * ldc + n] = acc ? C[m * ldc + n] + s : s;
+      }
+  }
+  void gemm_tn_acc(const float* A, int64_t lda, const float* S, int64_t lds, float* out, int N, int Kd, int64_t M, float*, int64_t) {
+    std::vector<double> acc((size_t)N * Kd, 0.0);
+    for (int64_t m = 0; m < M; ++m)
+      for (int n = 0; n < N; ++n) {
+        double a = A[m * lda + n];
+        for (int k = 0; k < Kd; ++k) acc[(size_t)n * Kd + k] += a * S[m * lds + k];
+      }
+    for (size_t i = 0; i < acc.size(); ++i) out[i] += (float)acc[i];
+  }
+  void wcolsum_acc(const float* Mat, int64_t ldm, int N, const float* Wt, int64_t M, float* out, float*, int64_t) {
+    int NE = Wt ? 4 : 1;
+    std::vector<double> acc((size_t)NE * N, 0.0);
+    for (int64_t r = 0; r < M; ++r)
+      for (int e = 0; e < NE; ++e) {
+        double w = Wt ? Wt[r * 4 + e] : 1.0;
+        for (int n = 0; n < N; ++n) acc[(size_t)e * N + n] += w * Mat[r * ldm + n];
+      }
+    for (size_t i = 0; i < acc.size(); ++i) out[i] += (float)acc[i];
+  }
+  void rowdot(const float* S, int64_t lds, const float* W, const float* b, float* U, int64_t M, int Hp, int o, int C) {
+    for (int64_t r = 0; r < M; ++r)
+      for (int m = 0; m < 4; ++m) {
+        float s = 0.f;
+        if (m < o) {
+          for (int j = 0; j < Hp; ++j) s += S[r * lds + j] * W[m * Hp + j];
+          if (r % C == 0) s += b[m];
+        }
+        U[r * 4 + m] = s;
+      }
+  }
+  void zero(void* p, size_t bytes) { memset(p, 0, bytes); }
+  void copy(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
+  bool is_device_ptr(const void*) { return true; }
+  const char* error() { return nullptr; }
+};
+}  // namespace
+
+DGMK_DEFINE_C_API(HostBackend, "host-emulation (tests only)")

@@ -1,0 +1,190 @@
+"""-m gpu: the CUDA path (through the C ABI) against the executed-reference golden
+vectors and the oracle.  Tolerance: 1e-5 relative on the loss and per-tensor norm-wise
+on the gradient (BASELINE.json north_star; SURVEY 7.3 H9 explains norm-wise)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, golden_names, rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def K():
+    from differential_equations_dnn_b200 import kernels, _cabi
+    _cabi.load()
+    return kernels
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def desc_of(g):
+    from differential_equations_dnn_b200 import _cabi
+    return _cabi.make_desc(*[int(v) for v in g["spec"]])
+
+
+def run(K, prob, g, ws=None, Bg=None):
+    d = desc_of(g)
+    th = dev(g["theta"])
+    if prob == "heat":
+        out = K.heat_step(d, th, *[dev(g[n]) for n in ("X", "X0", "XBD1", "XBD2", "x_bd1", "x_bd2")],
+                          B_global=Bg, ws=ws)
+    elif prob == "ode":
+        out = K.ode_step(d, th, dev(g["t"]), dev(g["t0"]), dev(g["y_ic"]), B_global=Bg, ws=ws)
+    elif prob == "fhn":
+        out = K.fhn_step(d, th, dev(g["t"]), dev(g["t0"]), dev(g["y_ic"]), B_global=Bg, ws=ws)
+    else:
+        out = K.fredholm_step(d, th, dev(g["x"]), dev(g["T"]), B_global=Bg, ws=ws)
+    out = out.cpu().numpy()
+    return float(out[-1]), out[:-1]
+
+
+def check(K, g, loss, grad, tol=TOL):
+    assert abs(loss - float(g["loss"])) <= tol * abs(float(g["loss"])), (loss, float(g["loss"]))
+    worst = 0.0
+    for off, r, c, live in K.param_layout(desc_of(g)):
+        n = r * max(c, 1)
+        ref, mine = g["grad"][off:off + n], grad[off:off + n]
+        assert np.all(np.isfinite(mine))
+        if not live:
+            assert np.all(mine == 0)
+        elif np.linalg.norm(ref) == 0:
+            assert np.linalg.norm(mine) < 1e-7
+        else:
+            worst = max(worst, rel(mine, ref))
+    assert worst < tol, worst
+
+
+PROBS = ("heat", "ode", "fhn", "fredholm")
+CASES = [(p, n) for p in PROBS for n in golden_names(p + "_") if "driver" not in n]
+
+
+@pytest.mark.parametrize("prob,name", CASES)
+def test_step_matches_reference(K, prob, name):
+    g = golden(name)
+    loss, grad = run(K, prob, g)
+    check(K, g, loss, grad)
+
+
+@pytest.mark.parametrize("prob,name", [("heat", "heat_dgm_h32l1"), ("fredholm", "fredholm_dgmraw_h32l1_k7"),
+                                       ("fhn", "fhn_dgm_h64l2"), ("ode", "ode_mlp_relu_h32l1")])
+def test_small_workspace_chunks(K, prob, name):
+    from differential_equations_dnn_b200 import _cabi
+    g = golden(name)
+    cls = {"heat": _cabi.WS_HEAT, "fhn": _cabi.WS_FHN, "fredholm": _cabi.WS_FREDHOLM, "ode": _cabi.WS_ODE}[prob]
+    k = g["T"].shape[0] if prob == "fredholm" else 0
+    small = K.workspace_bytes(desc_of(g), cls, 5, k)
+    ws = torch.empty(small, dtype=torch.uint8, device="cuda")
+    loss, grad = run(K, prob, g, ws=ws)
+    check(K, g, loss, grad)
+
+
+def test_dp_shards_sum(K):
+    g = golden("heat_dgm_h32l1")
+    B = g["X"].shape[0]
+    tl, tg = 0.0, 0.0
+    for lo, hi in ((0, 23), (23, B)):
+        sub = dict(g)
+        for n in ("X", "X0", "XBD1", "XBD2", "x_bd1", "x_bd2"):
+            sub[n] = g[n][lo:hi]
+        l, gr = run(K, "heat", sub, Bg=B)
+        tl, tg = tl + l, tg + gr
+    check(K, g, tl, tg)
+
+
+@pytest.mark.parametrize("name", golden_names("jets_"))
+def test_jets_and_eval(K, name):
+    g = golden(name)
+    d = desc_of(g)
+    th, X = dev(g["theta"]), dev(g["X"])
+    for order in (0, 1, 2):
+        Y, J, Hs, ws = K.jet_forward(d, th, X, order)
+        assert rel(Y.cpu().numpy(), g["y"]) < TOL
+        if order >= 1:
+            assert rel(J.cpu().numpy(), g["J"]) < TOL
+        if order >= 2:
+            assert rel(Hs.cpu().numpy(), g["Hs"]) < 5 * TOL
+    assert rel(K.evaluate(d, th, X).cpu().numpy(), g["y"]) < TOL
+
+
+@pytest.mark.parametrize("name", golden_names("jets_"))
+def test_jet_reverse_vs_oracle(K, name):
+    """Random cotangents on (Y, J, Hs): compare with the oracle's autograd."""
+    from oracle import ref_port as rp
+    g = golden(name)
+    d = desc_of(g)
+    spec = rp.NetSpec(*[int(v) for v in g["spec"]])
+    th = torch.from_numpy(g["theta"]).double().requires_grad_(True)
+    X = torch.from_numpy(g["X"]).double().requires_grad_(True)
+    y = rp.net_forward(spec, th, X)
+    B, o, dd = X.shape[0], spec.o, spec.d
+    gen = torch.Generator().manual_seed(11)
+    gY = torch.randn(B, o, generator=gen).double()
+    gJ = torch.randn(B, o, dd, generator=gen).double()
+    gH = torch.randn(B, o, dd, dd, generator=gen).double()
+    tot = (y * gY).sum()
+    for m in range(o):
+        gr = torch.autograd.grad(y[:, m].sum(), X, create_graph=True)[0]
+        tot = tot + (gr * gJ[:, m]).sum()
+        for i in range(dd):
+            hrow = torch.autograd.grad(gr[:, i].sum(), X, create_graph=True)[0]
+            tot = tot + (hrow * gH[:, m, i]).sum()
+    ref = torch.autograd.grad(tot, th)[0].numpy()
+    thd, Xd = dev(g["theta"]), dev(g["X"])
+    Y, J, Hs, ws = K.jet_forward(d, thd, Xd, 2)
+    grad = K.jet_reverse(d, thd, Xd, 2, dev(gY.numpy()), dev(gJ.numpy()), dev(gH.numpy()), ws).cpu().numpy()
+    for off, r, c, live in K.param_layout(d):
+        n = r * max(c, 1)
+        if np.linalg.norm(ref[off:off + n]) > 0:
+            assert rel(grad[off:off + n], ref[off:off + n]) < TOL
+
+
+def test_adam(K):
+    g = golden("adam_5steps")
+    th = dev(g["thetas"][0])
+    m, v = torch.zeros_like(th), torch.zeros_like(th)
+    live = torch.from_numpy(g["live"]).cuda()
+    for s in range(5):
+        K.adam_step(th, m, v, dev(g["grads"][s]), live, float(g["lr"]), 0.9, 0.999, 1e-8, s + 1)
+        assert rel(th.cpu().numpy(), g["thetas"][s + 1]) < 1e-6
+    assert rel(m.cpu().numpy(), g["m"]) < 1e-6 and rel(v.cpu().numpy(), g["v"]) < 1e-6
+    assert np.array_equal(th.cpu().numpy()[-5:], g["thetas"][0][-5:])  # dead params untouched
+
+
+def test_host_pointer_is_rejected(K):
+    import ctypes as C
+    from differential_equations_dnn_b200 import _cabi
+    lib = _cabi.load()
+    g = golden("ode_mlp_relu_h32l1")
+    d = desc_of(g)
+    th = np.ascontiguousarray(g["theta"], np.float32)
+    p = th.ctypes.data_as(C.c_void_p)
+    rc = lib.dgmk_ode_step(C.byref(d), p, p, p, p, 4, 4, p, p, p, 1 << 20, None)
+    assert rc == -4 and b"no CPU path" in lib.dgmk_last_error()
+    with pytest.raises(Exception):
+        K.ode_step(d, torch.from_numpy(th), torch.zeros(4, 1), torch.zeros(4, 1), torch.zeros(4, 1))
+
+
+def test_vs_oracle_midsize(K):
+    """B = 4096 heat + dgm_net.DGM(2,1,64,2): CUDA vs the torch-autograd oracle port."""
+    from oracle import ref_port as rp
+    from differential_equations_dnn_b200 import _cabi
+    spec = rp.NetSpec(rp.KIND_DGM_LINEAR, 2, 1, 64, 2, rp.ACT_TANH)
+    gen = torch.Generator().manual_seed(3)
+    theta = (torch.rand(spec.num_params(), generator=gen) - 0.5) * 0.3
+    B = 4096
+    x = torch.pi * torch.rand(B, 1, generator=gen)
+    t = 3 * torch.rand(B, 1, generator=gen)
+    z = torch.zeros(B, 1)
+    X, X0, B1, B2 = torch.cat([x, t], 1), torch.cat([x, z], 1), torch.cat([z, t], 1), torch.cat([z + torch.pi, t], 1)
+    loss_ref, g_ref = rp.loss_and_grad(rp.heat_loss, spec, theta, X, X0, B1, B2, z, z)
+    d = _cabi.make_desc(spec.kind, spec.d, spec.o, spec.H, spec.L, spec.act)
+    out = K.heat_step(d, theta.cuda(), X.cuda(), X0.cuda(), B1.cuda(), B2.cuda(), z.cuda(), z.cuda()).cpu().numpy()
+    assert abs(out[-1] - float(loss_ref)) <= TOL * abs(float(loss_ref))
+    for off, r, c, live in K.param_layout(d):
+        n = r * max(c, 1)
+        assert rel(out[off:off + n], g_ref.numpy()[off:off + n]) < TOL

@@ -1,0 +1,157 @@
+"""Pipeline orchestration (csrc/dgmk_pipeline.h, dgmk_capi_impl.h, dgmk_ops.h) compiled
+with a plain-loop host backend (tests/host_emul, TEST ONLY) against the executed-
+reference golden vectors.  Proves carving / ordering / packing / scaling before the
+GPU run; the CUDA kernels themselves are covered by the -m gpu tests."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden, golden_names, rel
+import importlib.util
+
+_spec = importlib.util.spec_from_file_location(
+    "_cabi_for_emul", os.path.join(ROOT, "differential_equations_dnn_b200", "_cabi.py"))
+cabi = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(cabi)
+
+EMUL = os.path.join(ROOT, "tests", "host_emul", "libdgmk_emul.so")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    subprocess.run([os.path.join(ROOT, "tests", "host_emul", "build.sh")], check=True)
+    return cabi.bind(C.CDLL(EMUL))
+
+
+def P(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def desc_of(g):
+    k, d, o, H, L, act = (int(v) for v in g["spec"])
+    return cabi.make_desc(k, d, o, H, L, act)
+
+
+def run_step(lib, prob, g, ws_bytes=None, Bg=None):
+    desc = desc_of(g)
+    theta = f32(g["theta"])
+    grad = np.full_like(theta, np.nan)
+    loss = np.zeros(1, np.float32)
+    if prob == "heat":
+        B = g["X"].shape[0]
+        cls, k = cabi.WS_HEAT, 0
+    elif prob in ("ode", "fhn"):
+        B = g["t"].shape[0]
+        cls, k = (cabi.WS_ODE if prob == "ode" else cabi.WS_FHN), 0
+    else:
+        B = g["x"].shape[0]
+        cls, k = cabi.WS_FREDHOLM, g["T"].shape[0]
+    Bg = Bg or B
+    need = lib.dgmk_workspace_bytes(C.byref(desc), cls, B, k)
+    assert need > 0
+    wsb = ws_bytes or need
+    ws = np.zeros(wsb // 4 + 16, np.float32)
+    if prob == "heat":
+        a = [f32(g[n]) for n in ("X", "X0", "XBD1", "XBD2", "x_bd1", "x_bd2")]
+        rc = lib.dgmk_heat_step(C.byref(desc), P(theta), *[P(z) for z in a], B, Bg, 1.0, P(loss), P(grad),
+                                P(ws), wsb, None)
+    elif prob in ("ode", "fhn"):
+        a = [f32(g[n]) for n in ("t", "t0", "y_ic")]
+        fn = lib.dgmk_ode_step if prob == "ode" else lib.dgmk_fhn_step
+        rc = fn(C.byref(desc), P(theta), *[P(z) for z in a], B, Bg, P(loss), P(grad), P(ws), wsb, None)
+    else:
+        x, T = f32(g["x"]), f32(g["T"])
+        rc = lib.dgmk_fredholm_step(C.byref(desc), P(theta), P(x), P(T), B, k, Bg, P(loss), P(grad), P(ws),
+                                    wsb, None)
+    assert rc == 0, lib.dgmk_last_error()
+    return float(loss[0]), grad
+
+
+def entry_slices(lib, desc):
+    n = lib.dgmk_param_layout(C.byref(desc), -1, None, None, None, None)
+    out = []
+    for i in range(n):
+        off, r, c, lv = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32()
+        assert lib.dgmk_param_layout(C.byref(desc), i, C.byref(off), C.byref(r), C.byref(c), C.byref(lv)) == 0
+        out.append((off.value, r.value * max(c.value, 1), lv.value))
+    return out
+
+
+def check(lib, g, loss, grad, tol=1e-5):
+    assert abs(loss - float(g["loss"])) <= tol * abs(float(g["loss"])), (loss, float(g["loss"]))
+    desc = desc_of(g)
+    assert lib.dgmk_param_count(C.byref(desc)) == g["theta"].size
+    worst = 0.0
+    for off, n, live in entry_slices(lib, desc):
+        ref = g["grad"][off:off + n]
+        mine = grad[off:off + n]
+        assert np.all(np.isfinite(mine))
+        if not live:
+            assert np.all(mine == 0) and not g["live"][off:off + n].any()
+            continue
+        if np.linalg.norm(ref) == 0:
+            assert np.linalg.norm(mine) < 1e-7
+        else:
+            worst = max(worst, rel(mine, ref))
+    assert worst < tol, worst
+
+
+PROBS = ("heat", "ode", "fhn", "fredholm")
+CASES = [(p, n) for p in PROBS for n in golden_names(p + "_") if "driver" not in n]
+
+
+@pytest.mark.parametrize("prob,name", CASES)
+def test_step_matches_reference(lib, prob, name):
+    g = golden(name)
+    loss, grad = run_step(lib, prob, g)
+    check(lib, g, loss, grad)
+
+
+@pytest.mark.parametrize("prob,name", [("heat", "heat_dgm_h32l1"), ("fredholm", "fredholm_dgmraw_h32l1_k7"),
+                                       ("fhn", "fhn_dgm_h64l2")])
+def test_chunked_equals_unchunked(lib, prob, name):
+    """A workspace too small for the batch forces several chunks; results must agree."""
+    g = golden(name)
+    desc = desc_of(g)
+    cls = {"heat": cabi.WS_HEAT, "fhn": cabi.WS_FHN, "fredholm": cabi.WS_FREDHOLM}[prob]
+    k = g["T"].shape[0] if prob == "fredholm" else 0
+    small = lib.dgmk_workspace_bytes(C.byref(desc), cls, 7, k)
+    loss, grad = run_step(lib, prob, g, ws_bytes=small)
+    check(lib, g, loss, grad)
+
+
+def test_data_parallel_shards_sum_to_global(lib):
+    """each rank scales by 1/B_global; SUM over ranks == single-process result."""
+    g = golden("heat_dgm_h32l1")
+    B = g["X"].shape[0]
+    tot_l, tot_g = 0.0, 0.0
+    for lo, hi in ((0, 40), (40, B)):
+        sub = dict(g)
+        for n in ("X", "X0", "XBD1", "XBD2", "x_bd1", "x_bd2"):
+            sub[n] = g[n][lo:hi]
+        l, gr = run_step(lib, "heat", sub, Bg=B)
+        tot_l, tot_g = tot_l + l, tot_g + gr
+    check(lib, g, tot_l, tot_g)
+
+
+def test_errors(lib):
+    g = golden("ode_mlp_relu_h32l1")
+    desc = desc_of(g)
+    bad = cabi.make_desc(0, 3, 1, 32, 1, 0)
+    assert lib.dgmk_param_count(C.byref(bad)) == -1
+    assert b"input_dim" in lib.dgmk_last_error()
+    theta = f32(g["theta"])
+    ws = np.zeros(64, np.float32)
+    loss = np.zeros(1, np.float32)
+    a = [f32(g[n]) for n in ("t", "t0", "y_ic")]
+    rc = lib.dgmk_ode_step(C.byref(desc), P(theta), *[P(z) for z in a], 64, 64, P(loss), P(theta.copy()), P(ws), 256, None)
+    assert rc == -2  # DGMK_EWORKSPACE
+    rc = lib.dgmk_heat_step(C.byref(desc), P(theta), *[P(theta)] * 6, 64, 64, 1.0, P(loss), P(theta), P(ws), 256, None)
+    assert rc == -1  # wrong dims for heat
