@@ -56,7 +56,13 @@ _SIGNATURES = {
     "dgmk_adam": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
                             C.c_int64, _P]),
 }
-EXPORTS = tuple(_SIGNATURES)
+# diagnostics exported only by the CUDA library (bench.py)
+_CUDA_ONLY = {
+    "dgmk_launch_count": (C.c_ulonglong, []),
+    "dgmk_ffma_probe": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
+    "dgmk_gemm_probe": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int64, _P]),
+}
+EXPORTS = tuple(_SIGNATURES) + tuple(_CUDA_ONLY)
 
 
 def bind(lib):
@@ -79,6 +85,9 @@ def load():
                 f"{LIB_PATH} not found: build it with `python __graft_entry__.py build` "
                 "(nvcc, sm_100a). This package has no CPU or PyTorch fallback.")
         lib = bind(C.CDLL(LIB_PATH))
+        for name, (res, args) in _CUDA_ONLY.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
         if lib.dgmk_backend() != BACKEND:
             raise DgmkError(f"{LIB_PATH} reports backend {lib.dgmk_backend()!r}, expected {BACKEND!r}")
         _LIB = lib

@@ -10,6 +10,10 @@ namespace dgmk {
 
 constexpr int EW_THREADS = 256;
 
+// number of kernels this library has launched in this process (diagnostic: bench.py
+// reports it as gpu_launches)
+static unsigned long long g_launches = 0;
+
 template <class F>
 __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const F f, int64_t n) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -112,7 +116,7 @@ struct CudaBackend {
     }
   }
   void note(cudaError_t e) { if (e != cudaSuccess && !err) err = cudaGetErrorString(e); }
-  void post() { note(cudaPeekAtLastError()); }
+  void post() { ++g_launches; note(cudaPeekAtLastError()); }
 
   template <class F>
   void ew(const F& f, int64_t n) {
@@ -200,9 +204,48 @@ struct CudaBackend {
     if (e != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
   }
-  const char* error() { post(); return err; }
+  const char* error() { note(cudaPeekAtLastError()); return err; }
 };
 
 }  // namespace dgmk
 
 DGMK_DEFINE_C_API(dgmk::CudaBackend, "cuda-sm100a")
+
+// ---- diagnostics (not part of the reference-facing surface) -------------------------
+namespace dgmk {
+// dependent-chain FFMA: 16 independent accumulators per thread, operands in registers
+__global__ void __launch_bounds__(256) ffma_probe_kernel(float* out, const float* in, int iters) {
+  float acc[16];
+  float b = in[threadIdx.x % 7], c = in[threadIdx.x % 5 + 1];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = in[i];
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], b, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace dgmk
+
+extern "C" {
+unsigned long long dgmk_launch_count(void) { return dgmk::g_launches; }
+// FP32 FFMA peak probe: launches blocks x 256 threads, each doing 64*iters FFMAs.
+// `in` >= 32 floats, `out` >= blocks*256 floats (device).  flops = 2*64*iters*256*blocks.
+int dgmk_ffma_probe(const float* in, float* out, int blocks, int iters, void* stream) {
+  dgmk::ffma_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, in, iters);
+  return cudaPeekAtLastError() == cudaSuccess ? 0 : DGMK_ECUDA;
+}
+// The dominant GEMM tile stand-alone (same kernel the pipeline launches) for the live
+// roofline measurement in bench.py: C[M,N] = A[M,K] B[K,N], lda = ldc = ld.
+int dgmk_gemm_probe(const float* A, const float* B, float* C, int64_t M, int N, int K, int64_t ld, void* stream) {
+  if (N % 32 || K % 16) return DGMK_EINVAL;
+  dgmk::CudaBackend bk(stream);
+  bk.gemm_nn(A, ld, B, N, C, ld, M, N, K, false);
+  return bk.error() ? DGMK_ECUDA : 0;
+}
+}

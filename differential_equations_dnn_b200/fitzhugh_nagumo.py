@@ -1,0 +1,75 @@
+"""Drop-in for the hot path of the reference's fitzhugh_nagumo.py (two-variable ODE system).
+
+Same names / signatures as fitzhugh_nagumo.py:38-177; the loss runs in dgmk_fhn_step.
+"""
+import numpy as np
+import torch
+
+from . import autograd as ag
+from . import parallel
+from ._flat import deferred_forward
+from .auxiliary_funs import fn_timer
+from .heat import _device
+from .optim import FusedAdam
+from .simple_ode import _calls
+
+IEXT, ALPHA, BETA, TAU = 0.5, 0.7, 0.8, 2.5  # fitzhugh_nagumo.py:69-70
+
+
+def FZNFun(y, t, I, alpha, beta, tau):
+    """Right-hand side for scipy.odeint (fitzhugh_nagumo.py:38-50)."""
+    return np.array([y[0] - y[0] ** 3 / 3 - y[1] + I, (y[0] + alpha - beta * y[1]) / tau])
+
+
+def dgm_loss_func(y, y0, t, y_ic):
+    """mean(r_Y^2) + mean(r_W^2) + mean((y0 - y_ic)^2), r_Y = Y' + Y^3/3 + W - I - Y,
+    r_W = W' + (beta W - alpha - Y)/tau (fitzhugh_nagumo.py:53-97; the last mean runs
+    over 2B elements)."""
+    call = _calls(y, y0)
+    if call is not None:
+        net, tt, tt0 = call
+        return ag.FhnStepFn.apply(net, tt, tt0, y_ic, *ag.params_of(net))
+    Y, W = y[:, 0:1], y[:, 1:2]
+    ones = torch.ones_like(Y)
+    dY = torch.autograd.grad(Y, t, grad_outputs=ones, create_graph=True, retain_graph=True)[0]
+    dW = torch.autograd.grad(W, t, grad_outputs=ones, create_graph=True, retain_graph=True)[0]
+    Lx = torch.mean((dY + (Y ** 3 / 3.0 + W - IEXT - Y)) ** 2)
+    Ly = torch.mean((dW + (BETA * W - ALPHA - Y) / TAU) ** 2)
+    return Lx + Ly + torch.mean((y0 - y_ic) ** 2)
+
+
+@fn_timer
+def minimize_loss_dgm(net, y_ic, iterations=1000, batch_size=32, lrate=1e-4, sampler="grid"):
+    """fitzhugh_nagumo.py:100-156.  sampler="grid" is the shipped one: `batch_size` (<=200)
+    distinct nodes of a 200-point grid on [0,30] (:123-133); sampler="uniform" is the
+    commented-out `30.01 * rand` (:129), the only one that scales past 200 rows."""
+    device = _device()
+    optimizer = FusedAdam(net.parameters(), lr=lrate)
+    t0 = torch.zeros([batch_size, 1], device=device)
+    num_samples = 200
+    T = torch.linspace(0.0, 30.0, steps=num_samples, device=device)
+    prob = torch.full((num_samples,), 1.0 / num_samples, device=device)
+    losses = []
+    for i in range(iterations):
+        if sampler == "grid":
+            t = T[prob.multinomial(num_samples=batch_size, replacement=False)].reshape(-1, 1)
+        else:
+            t = 30.01 * torch.rand([batch_size, 1], device=device)
+        optimizer.zero_grad()
+        with deferred_forward(net):
+            y, y0 = net(t), net(t0)
+        loss = dgm_loss_func(y, y0, t, y_ic)
+        loss.backward()
+        optimizer.step()
+        losses.append(loss.detach())
+        if i % 100 == 0 and parallel.rank() == 0:
+            print(f"Iteration: {i}, Loss: {loss.item()}, LR: {optimizer.param_groups[0]['lr']}")
+    return net, (torch.stack(losses).cpu().tolist() if losses else [])
+
+
+def gridEvaluation(net, nodes=10):
+    """net on `nodes` points of [0,30] -> [nodes, 2] (fitzhugh_nagumo.py:159-177)."""
+    t = torch.linspace(0.0, 30.0, nodes, dtype=torch.float64).float().reshape(-1, 1).to(_device())
+    net.eval()
+    with torch.no_grad():
+        return net(t).double().cpu().numpy()

@@ -1,0 +1,65 @@
+"""Drop-in for the hot path of the reference's fredholm.py:
+y(x) = sin x + int_0^{pi/2} sin x cos t y(t) dt, Monte-Carlo integral with k fresh nodes
+per point per step (fredholm.py:47-74).  Same names / signatures; the loss runs in
+dgmk_fredholm_step.
+"""
+import numpy as np
+import torch
+
+from . import autograd as ag
+from . import parallel
+from ._flat import FlatParamModule
+from .auxiliary_funs import fn_timer
+from .heat import _device
+from .optim import FusedAdam
+
+
+def exact_solution(x):
+    """2 sin x (fredholm.py:40-44)."""
+    return 2.0 * np.sin(x)
+
+
+def draw_nodes(x, k):
+    """The k Monte-Carlo node sets, in the order the reference's loop draws them
+    (`pi/2 * rand_like(x)`, fredholm.py:66-67) -> [k, B, 1]."""
+    return torch.stack([np.pi / 2.0 * torch.rand_like(x) for _ in range(k)])
+
+
+def dgm_loss_func(net, x, k=50, nodes=None):
+    """mean[(net(x) - sin x - (pi/2k) sum_j sin x cos t_j net(t_j))^2] (fredholm.py:47-74).
+    `nodes` ([k,B,1]) lets a caller supply the draws (parity tests, data-parallel
+    shards); by default they are drawn here exactly like the reference does."""
+    if nodes is None:
+        nodes = draw_nodes(x.detach(), k)
+    if isinstance(net, FlatParamModule):
+        return ag.FredholmStepFn.apply(net, x, nodes, *ag.params_of(net))
+    dr = np.pi / (2 * nodes.shape[0])
+    integral = 0.0
+    for t in nodes:
+        integral = integral + torch.sin(x) * torch.cos(t) * net(t)
+    return torch.mean((net(x) - torch.sin(x) - integral * dr) ** 2)
+
+
+@fn_timer
+def minimize_loss_dgm(net, y_ic=2.0, iterations=1000, batch_size=32, lrate=1e-4, k=50):
+    """fredholm.py:77-117 (y_ic is accepted and unused, as there)."""
+    device = _device()
+    optimizer = FusedAdam(net.parameters(), lr=lrate)
+    losses = []
+    for i in range(iterations):
+        t = np.pi / 2.0 * torch.rand([batch_size, 1], device=device)
+        optimizer.zero_grad()
+        loss = dgm_loss_func(net, t, k)
+        loss.backward()
+        optimizer.step()
+        losses.append(loss.detach())
+        if i % 100 == 0 and parallel.rank() == 0:
+            print(f"Iteration: {i}, Loss: {loss.item()}, LR: {optimizer.param_groups[0]['lr']}")
+    return net, (torch.stack(losses).cpu().tolist() if losses else [])
+
+
+def gridEvaluation(net, nodes=10, y_ic=2.0):
+    """net on `nodes` points of [0, pi/2] (fredholm.py:120-138)."""
+    t = torch.linspace(0, np.pi / 2.0, nodes, dtype=torch.float64).float().reshape(-1, 1).to(_device())
+    with torch.no_grad():
+        return net(t)[:, 0].double().cpu().numpy()

@@ -1,0 +1,97 @@
+"""Drop-in for the hot path of the reference's heat.py: 1-D heat equation u_t = k u_xx.
+
+`dgm_loss_func`, `minimize_loss_dgm`, `gridEvaluation`, `exact_solution` keep the
+reference's names, argument order and return types (heat.py:36-172).  The loss is one
+fused kernel sequence (include/dgmk.h: dgmk_heat_step) instead of four network
+evaluations and two nested torch.autograd.grad sweeps.
+"""
+import numpy as np
+import torch
+
+from . import autograd as ag
+from . import parallel
+from ._flat import DeferredOutput, FlatParamModule, deferred_forward  # noqa: F401
+from .auxiliary_funs import fn_timer
+from .optim import FusedAdam
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise ag.DgmkError("no CUDA device: differential_equations_dnn_b200 has no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def exact_solution(k=1, nodes=10):
+    """sin(x) exp(-k t) on the (t, x) grid [0,3] x [0,pi] (heat.py:36-47)."""
+    t = np.linspace(0, 3, nodes)[:, None]
+    x = np.linspace(0, np.pi, nodes)[None, :]
+    return np.sin(x) * np.exp(-k * t)
+
+
+def dgm_loss_func(net, x, x0, xbd1, xbd2, x_bd1, x_bd2):
+    """mean[(u_t - k u_xx)^2 + (u(x,0) - sin x)^2 + (u(0,t) - x_bd1)^2 + (u(pi,t) - x_bd2)^2]
+    with k = 1 (heat.py:50-95).  Returns a 0-dim tensor; `.backward()` fills `.grad`."""
+    if isinstance(net, FlatParamModule):
+        return ag.HeatStepFn.apply(net, x, x0, xbd1, xbd2, x_bd1, x_bd2, 1.0, *ag.params_of(net))
+    return reference_style_loss(net, x, x0, xbd1, xbd2, x_bd1, x_bd2)
+
+
+def reference_style_loss(net, x, x0, xbd1, xbd2, x_bd1, x_bd2, kappa=1.0):
+    """The same loss written against the module-level seam (nested autograd.grad on
+    `net(x)`); works for any differentiable `net`, and for ours it exercises
+    JetFn/Link0/Link1.  Used by the parity tests of seam S1."""
+    y = net(x)
+    ones = torch.ones_like(y)
+    dy = torch.autograd.grad(y, x, grad_outputs=ones, create_graph=True, retain_graph=True)[0]
+    u_t, u_x = dy[:, 1:2], dy[:, 0:1]
+    u_xx = torch.autograd.grad(u_x, x, grad_outputs=ones, create_graph=True, retain_graph=True)[0][:, 0:1]
+    res = (u_t - kappa * u_xx) ** 2
+    res = res + (net(x0) - torch.sin(x0[:, 0:1])) ** 2
+    res = res + (net(xbd1) - x_bd1) ** 2 + (net(xbd2) - x_bd2) ** 2
+    return res.mean()
+
+
+@fn_timer
+def minimize_loss_dgm(net, iterations=1000, batch_size=32, lrate=1e-4):
+    """The reference's training driver (heat.py:98-149): same sampler, same Adam
+    defaults, returns (net, train_loss: list[float]).  Differences that do not change
+    results: losses stay on the device and are read back once at the end (plus every
+    100th for the progress print) instead of a host sync per step (heat.py:143); under
+    `parallel.enable_data_parallel()` each rank draws its own rows and the gradient is
+    all-reduced inside `dgm_loss_func`."""
+    device = _device()
+    optimizer = FusedAdam(net.parameters(), lr=lrate)
+    t0 = torch.zeros([batch_size, 1], device=device)
+    xbd1 = torch.zeros([batch_size, 1], device=device)
+    xbd2x = torch.ones([batch_size, 1], device=device) * torch.pi
+    xbd2y = torch.zeros([batch_size, 1], device=device)
+    losses = []
+    for i in range(iterations):
+        x = torch.pi * torch.rand([batch_size, 1], device=device)
+        t = 3.0 * torch.rand([batch_size, 1], device=device)
+        X = torch.cat([x, t], dim=1)
+        X0 = torch.cat([x, t0], dim=1)
+        X_BD1 = torch.cat([xbd1, t], dim=1)
+        X_BD2 = torch.cat([xbd2x, t], dim=1)
+        optimizer.zero_grad()
+        loss = dgm_loss_func(net, X, X0, X_BD1, X_BD2, xbd1, xbd2y)
+        loss.backward()
+        optimizer.step()
+        losses.append(loss.detach())
+        if i % 100 == 0 and parallel.rank() == 0:
+            print(f"Iteration: {i}, Loss: {loss.item()}, LR: {optimizer.param_groups[0]['lr']}")
+    train_loss = torch.stack(losses).cpu().tolist() if losses else []
+    return net, train_loss
+
+
+def gridEvaluation(net, nodes=10):
+    """net on the nodes x nodes (t, x) grid (heat.py:152-172): one batched value-only
+    launch instead of nodes^2 single-row forwards."""
+    device = _device()
+    t = torch.linspace(0, 3.0, nodes, dtype=torch.float64)
+    x = torch.linspace(0, np.pi, nodes, dtype=torch.float64)
+    T, Xg = torch.meshgrid(t, x, indexing="ij")
+    pts = torch.stack([Xg.reshape(-1), T.reshape(-1)], 1).float().to(device)
+    with torch.no_grad():
+        y = net(pts)
+    return y.reshape(nodes, nodes).double().cpu().numpy()

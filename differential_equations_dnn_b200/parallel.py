@@ -1,0 +1,133 @@
+"""Data parallelism over collocation rows and one-trial-per-GPU sweeps.
+
+The reference is single-GPU.  Rows are independent (no batch-norm on the
+hot path), so the only exchange per step is a SUM all-reduce of the flat FP32 buffer
+[grad_theta (P) | loss (1)] -- 0.8 MB for dgm_net.DGM(2,1,128,3) -- over NCCL/NVLink;
+every rank then applies the identical fused Adam update, so no broadcast is needed
+(SURVEY 8e).  Each rank's kernels already scale by 1/B_global.
+
+Hyper-parameter sweeps (optimize_heat_ray.py:133-203, batchsize_effect_heat.py:186-202)
+are "replicas only": one process per GPU, no communication until the final gather.
+"""
+from __future__ import annotations
+
+import os
+import random
+
+import torch
+import torch.distributed as dist
+
+_STATE = {"group": None, "enabled": False, "bglobal": {}}
+
+
+def enable_data_parallel(group=None):
+    """Shard every subsequent fused step over `group` (default: WORLD)."""
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised")
+    _STATE.update(group=group, enabled=True, bglobal={})
+
+
+def disable_data_parallel():
+    _STATE.update(group=None, enabled=False, bglobal={})
+
+
+def is_enabled():
+    return _STATE["enabled"]
+
+
+def world_size():
+    return dist.get_world_size(_STATE["group"]) if _STATE["enabled"] else 1
+
+
+def rank():
+    return dist.get_rank(_STATE["group"]) if _STATE["enabled"] else 0
+
+
+def global_batch(B_local, device):
+    """Sum of the ranks' local row counts (cached per local size: shards are static)."""
+    if not _STATE["enabled"]:
+        return B_local
+    Bg = _STATE["bglobal"].get(B_local)
+    if Bg is None:
+        t = torch.tensor([B_local], dtype=torch.int64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_STATE["group"])
+        Bg = int(t.item())
+        _STATE["bglobal"][B_local] = Bg
+    return Bg
+
+
+def reduce_step(launch, B_local, device=None):
+    """Run `launch(B_global) -> [P+1] tensor` on this rank's rows and SUM it over ranks.
+
+    `launch` is the fused step (kernels.*_step) in the product and the oracle in the
+    gloo CPU tests; the collective logic is the same."""
+    if not _STATE["enabled"]:
+        return launch(None)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() \
+            else torch.device("cpu")
+    Bg = global_batch(B_local, device)
+    out = launch(Bg)
+    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=_STATE["group"])
+    return out
+
+
+def shard(t, dim=0):
+    """This rank's contiguous block of rows (rank r gets [r*B/R, (r+1)*B/R))."""
+    if not _STATE["enabled"]:
+        return t
+    R, r = world_size(), rank()
+    B = t.shape[dim]
+    lo, hi = (B * r) // R, (B * (r + 1)) // R
+    return t.narrow(dim, lo, hi - lo)
+
+
+# ---- independent trials, one per GPU (no Ray) -------------------------------------
+def sample_search_space(n, seed=0):
+    """n configs from the space of optimize_heat_ray.py:173-176:
+    batch_size ~ randint[1,512), n_iters ~ randint[1000,50000), lrate ~ loguniform(1e-4,1e-1)."""
+    import math
+    rng = random.Random(seed)
+    out = []
+    for _ in range(n):
+        out.append({"batch_size": rng.randrange(1, 512), "n_iters": rng.randrange(1000, 50000),
+                    "lrate": math.exp(rng.uniform(math.log(1e-4), math.log(1e-1)))})
+    return out
+
+
+def run_trials(objective, configs):
+    """Round-robin `configs` over the ranks (one GPU each, zero communication while
+    training), gather `{config, loss}` records on every rank.  `objective(config)`
+    returns the final loss, like objectiveRay -> session.report (optimize_heat_ray.py:157)."""
+    if dist.is_initialized():
+        R, r = dist.get_world_size(), dist.get_rank()
+    else:
+        R, r = 1, 0
+    mine = [(i, c) for i, c in enumerate(configs) if i % R == r]
+    results = [{"trial": i, "config": c, "loss": float(objective(c)), "rank": r} for i, c in mine]
+    if R > 1:
+        gathered = [None] * R
+        dist.all_gather_object(gathered, results)
+        results = [x for part in gathered for x in part]
+    results.sort(key=lambda d: d["trial"])
+    return results
+
+
+def best_trial(results):
+    """tune.ResultGrid.get_best_result(metric='loss', mode='min') (optimize_heat_ray.py:199-201)."""
+    return min(results, key=lambda d: d["loss"])
+
+
+def init_from_env(backend=None):
+    """torchrun-style init (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*); binds cuda:LOCAL_RANK."""
+    if dist.is_initialized():
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group(backend=backend)

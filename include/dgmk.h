@@ -127,6 +127,12 @@ int dgmk_eval(const dgmk_net_desc* desc, const float* theta, const float* x, int
 int dgmk_adam(float* theta, float* m, float* v, const float* grad, const uint8_t* live, int64_t P,
               double lr, double beta1, double beta2, double eps, int64_t step, void* stream);
 
+/* ---- diagnostics used by bench.py (not reference-facing) --------------------------- */
+unsigned long long dgmk_launch_count(void); /* kernels launched by this library so far */
+int dgmk_ffma_probe(const float* in, float* out, int blocks, int iters, void* stream);
+int dgmk_gemm_probe(const float* A, const float* B, float* C, int64_t M, int N, int K, int64_t ld,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

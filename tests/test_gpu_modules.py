@@ -1,0 +1,209 @@
+"""-m gpu: the drop-in Python layer (modules, autograd seams, losses, optimizer, drivers)
+on top of the CUDA library, against the executed-reference golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, golden_names, rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def build_net(g, seed=1234):
+    from differential_equations_dnn_b200 import neural_networks as nn_, dgm_net
+    kind, d, o, H, L, act = (int(v) for v in g["spec"])
+    torch.manual_seed(seed)
+    if kind == 0:
+        net = nn_.MLP(d, o, H, L, activation={0: "relu", 1: "sigmoid", 2: "tanh", 3: "leaky_relu"}[act])
+    elif kind == 1:
+        net = dgm_net.DGM(d, o, H, L)
+    else:
+        net = nn_.DGM(d, o, H, L)
+    assert np.array_equal(net.flat_theta().numpy(), g["theta"]), "same seed must give the reference's weights"
+    return net.cuda()
+
+
+def cu(g, *keys):
+    return [torch.from_numpy(g[k]).cuda() for k in keys]
+
+
+def check_grads(net, g, tol=TOL):
+    off = 0
+    for name, p in net.named_parameters():
+        n = p.numel()
+        ref = g["grad"][off:off + n]
+        if not g["live"][off]:
+            assert p.grad is None, name            # reference leaves grad None (dgm1.*)
+        elif np.linalg.norm(ref) == 0:
+            assert p.grad is None or p.grad.abs().max().item() < 1e-7
+        else:
+            assert rel(p.grad.reshape(-1).cpu().numpy(), ref) < tol, name
+        off += n
+
+
+HEAT_KEYS = ("X", "X0", "XBD1", "XBD2", "x_bd1", "x_bd2")
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names("heat_")])
+def test_heat_fast_path(name):
+    from differential_equations_dnn_b200 import heat
+    g = golden(name)
+    net = build_net(g)
+    loss = heat.dgm_loss_func(net, *cu(g, *HEAT_KEYS))
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= TOL * abs(float(g["loss"]))
+    check_grads(net, g)
+
+
+@pytest.mark.parametrize("name", ["heat_dgm_h32l1", "heat_mlp_tanh_h128l3", "heat_mlp_relu_h128l3",
+                                  "heat_mlp_sigmoid_h50l1", "heat_dgmraw_h32l2"])
+def test_heat_reference_code_on_our_module(name):
+    """Seam S1: the reference's formulation (nested autograd.grad on net(x)) runs
+    unmodified on our module and gives the reference's numbers."""
+    from differential_equations_dnn_b200 import heat
+    g = golden(name)
+    net = build_net(g)
+    a = cu(g, *HEAT_KEYS)
+    a[0].requires_grad_(True)
+    loss = heat.reference_style_loss(net, *a)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= TOL * abs(float(g["loss"]))
+    check_grads(net, g)
+
+
+@pytest.mark.parametrize("name", golden_names("ode_mlp") + golden_names("ode_dgm") + golden_names("fhn_"))
+@pytest.mark.parametrize("mode", ["deferred", "eager_traced", "generic"])
+def test_ode_fhn_three_paths(name, mode):
+    from differential_equations_dnn_b200 import simple_ode, fitzhugh_nagumo
+    from differential_equations_dnn_b200._flat import deferred_forward
+    g = golden(name)
+    mod = simple_ode if name.startswith("ode") else fitzhugh_nagumo
+    net = build_net(g)
+    t, t0, y_ic = cu(g, "t", "t0", "y_ic")
+    if mode == "deferred":
+        with deferred_forward(net):
+            y, y0 = net(t), net(t0)
+        loss = mod.dgm_loss_func(y, y0, t, y_ic)
+    elif mode == "eager_traced":
+        t.requires_grad_(True)
+        y, y0 = net(t), net(t0)
+        loss = mod.dgm_loss_func(y, y0, t, y_ic)
+    else:  # break the trace: plain tensors -> reference formulation through autograd (seam S1)
+        t.requires_grad_(True)
+        y, y0 = net(t) * 1.0, net(t0) * 1.0
+        loss = mod.dgm_loss_func(y, y0, t, y_ic)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= TOL * abs(float(g["loss"]))
+    check_grads(net, g)
+
+
+@pytest.mark.parametrize("name", golden_names("fredholm_"))
+def test_fredholm(name):
+    from differential_equations_dnn_b200 import fredholm
+    g = golden(name)
+    net = build_net(g)
+    x, T = cu(g, "x", "T")
+    loss = fredholm.dgm_loss_func(net, x, k=T.shape[0], nodes=T)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= TOL * abs(float(g["loss"]))
+    check_grads(net, g)
+    # default path draws its own nodes: just has to run and be finite
+    l2 = fredholm.dgm_loss_func(net, x, k=7)
+    assert np.isfinite(l2.item())
+
+
+def test_reference_driver_trajectory():
+    """30 iterations of simple_ode.minimize_loss_dgm replayed with the reference's own
+    sample sequence: losses and final weights track the reference (Adam included)."""
+    from differential_equations_dnn_b200 import neural_networks as nn_, simple_ode
+    from differential_equations_dnn_b200._flat import deferred_forward
+    from differential_equations_dnn_b200.optim import FusedAdam
+    g = golden("ode_driver_30its")
+    torch.manual_seed(0)
+    net = nn_.MLP(input_dim=1, output_dim=1, hidden_size=32)
+    assert np.array_equal(net.flat_theta().numpy(), g["theta0"])
+    net = net.cuda()
+    opt = FusedAdam(net.parameters(), lr=1e-4)
+    y_ic = torch.ones(64, 1, device="cuda") * 2.0
+    t0 = torch.zeros(64, 1, device="cuda")
+    losses = []
+    for i in range(30):
+        t = torch.from_numpy(g["ts"][i]).cuda()
+        opt.zero_grad()
+        with deferred_forward(net):
+            y, y0 = net(t), net(t0)
+        loss = simple_ode.dgm_loss_func(y, y0, t, y_ic)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert rel(np.array(losses), g["losses"]) < 1e-5
+    assert rel(net.flat_theta().cpu().numpy(), g["theta_end"]) < 1e-6
+
+
+def test_module_contract():
+    from differential_equations_dnn_b200 import dgm_net, neural_networks as nn_
+    torch.manual_seed(3)
+    net = dgm_net.DGM(2, 1, 32, 2)
+    keys = list(net.state_dict().keys())
+    assert keys[:2] == ["S_in.weight", "S_in.bias"] and "layers.1.H_uh.weight" in keys and keys[-1] == "S_out.bias"
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.cuda()
+    th = net.flat_theta()
+    assert th.is_cuda and all(p.data_ptr() >= th.data_ptr() for p in net.parameters())
+    x = torch.rand(5, 2, device="cuda")
+    with torch.no_grad():
+        y = net(x)
+    assert y.shape == (5, 1)
+    net2 = dgm_net.DGM(2, 1, 32, 2).cuda()
+    net2.load_state_dict(sd)
+    with torch.no_grad():
+        assert torch.equal(net2(x), y)
+    # in-place edits through a parameter are seen by the kernels (views of one buffer)
+    with torch.no_grad():
+        net2.S_out.bias.add_(1.0)
+        assert torch.allclose(net2(x), y + 1.0, atol=1e-6)
+    # 1-D input like the reference's gridEvaluation (simple_ode.py:128-131)
+    m = nn_.MLP(input_dim=1, output_dim=1, hidden_size=32).cuda()
+    with torch.no_grad():
+        assert m(torch.ones(1, device="cuda") * 0.3).shape == (1,)
+    with pytest.raises(Exception):
+        dgm_net.DGM(2, 1, 8, 1)(torch.zeros(2, 2))  # CPU tensors: no fallback
+
+
+def test_eval_matches_oracle():
+    from oracle import ref_port as rp
+    g = golden("heat_dgm_h50l3")
+    net = build_net(g)
+    X = torch.from_numpy(g["X"])
+    ref = rp.net_forward(rp.NetSpec(*[int(v) for v in g["spec"]]), torch.from_numpy(g["theta"]), X)
+    with torch.no_grad():
+        assert rel(net(X.cuda()).cpu().numpy(), ref.numpy()) < TOL
+
+
+def test_simple_ode_end_to_end():
+    """BASELINE config 1 end to end: 5000 its x 64 (simple_ode.py defaults), MAE vs 2exp(-t)
+    on 25 nodes.  Reference (CPU, seed 0): MAE 0.00253; criterion: within 1e-3 of it."""
+    from differential_equations_dnn_b200 import neural_networks as nn_, simple_ode
+    torch.manual_seed(0)
+    net = nn_.MLP(input_dim=1, output_dim=1, hidden_size=32).cuda()
+    net, losses = simple_ode.minimize_loss_dgm(net, y_ic=2.0, iterations=5000, batch_size=64, lrate=1e-4)
+    assert len(losses) == 5000 and losses[-1] < losses[0]
+    sol = simple_ode.gridEvaluation(net, nodes=25)
+    mae = np.abs(sol - simple_ode.exact_solution(np.linspace(0, 1.0, 25))).mean()
+    assert abs(mae - 0.00253) < 1e-3 + 0.00253, mae   # same ballpark as the reference, never worse by 1e-3
+    assert mae < 0.00253 + 1e-3, mae
+
+
+def test_heat_end_to_end_dgm():
+    """heat + dgm_net.DGM(2,1,32,1), 15000 its x 64, lr 1e-4 (heat.py driver), 40x40 grid.
+    Reference seeds 0/1/2: MAE 2.0e-4 / 2.2e-4 / 4.1e-4; criterion 1e-3."""
+    from differential_equations_dnn_b200 import dgm_net, heat
+    torch.manual_seed(0)
+    net = dgm_net.DGM(input_dim=2, output_dim=1, hidden_size=32, num_layers=1).cuda()
+    net, losses = heat.minimize_loss_dgm(net, iterations=15000, batch_size=64, lrate=1e-4)
+    sol = heat.gridEvaluation(net, nodes=40)
+    err = sol - heat.exact_solution(nodes=40)
+    mae, rmse = np.abs(err).mean(), np.sqrt((err ** 2).mean())
+    print("heat e2e: final loss", losses[-1], "MAE", mae, "RMSE", rmse)
+    assert mae < 2.0e-4 + 1e-3 and rmse < 2.5e-4 + 1e-3
