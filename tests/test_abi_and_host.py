@@ -1,0 +1,122 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/dgmk.h
+declares (no compute without a GPU), layouts agree between Python, the C ABI and the
+oracle, and the drop-in modules keep the reference's contract."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, golden, golden_names
+
+
+@pytest.fixture(scope="module")
+def cabi():
+    from differential_equations_dnn_b200 import _cabi
+    _cabi.build()   # nvcc cross-compiles sm_100a without a GPU
+    return _cabi
+
+
+def test_library_exports_every_declared_symbol(cabi):
+    hdr = open(os.path.join(ROOT, "include", "dgmk.h")).read()
+    declared = set(re.findall(r"\b(dgmk_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"dgmk_net_desc"}
+    assert declared, "no declarations parsed"
+    lib = C.CDLL(cabi.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/dgmk.h but not exported"
+    assert declared == set(cabi.EXPORTS), declared ^ set(cabi.EXPORTS)
+    lib = cabi.load()
+    assert lib.dgmk_version() == 100 and lib.dgmk_backend() == b"cuda-sm100a"
+
+
+def test_sass_is_sm100a(cabi):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", cabi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_missing_library_fails_loudly(cabi, monkeypatch):
+    monkeypatch.setattr(cabi, "_LIB", None)
+    monkeypatch.setattr(cabi, "LIB_PATH", "/nonexistent/libdgmk.so")
+    with pytest.raises(cabi.DgmkError, match="no CPU or PyTorch fallback"):
+        cabi.load()
+
+
+@pytest.mark.parametrize("name", [n for p in ("heat_", "ode_", "fhn_", "fredholm_") for n in golden_names(p)
+                                  if "driver" not in n])
+def test_layouts_agree(cabi, name):
+    from oracle import ref_port as rp
+    from differential_equations_dnn_b200 import kernels
+    g = golden(name)
+    spec = rp.NetSpec(*[int(v) for v in g["spec"]])
+    d = cabi.make_desc(*[int(v) for v in g["spec"]])
+    assert kernels.param_count(d) == spec.num_params() == g["theta"].size
+    lay = kernels.param_layout(d)
+    off = 0
+    for (o, r, c, live), (nm, shape, olive) in zip(lay, spec.entries()):
+        assert o == off and ((r,) if c == 0 else (r, c)) == tuple(shape) and live == olive, nm
+        off += int(np.prod(shape))
+    assert len(lay) == len(spec.entries())
+    assert kernels.workspace_bytes(d, cabi.WS_HEAT if spec.d == 2 else cabi.WS_ODE if spec.o == 1 else cabi.WS_FHN, 1024) > 0
+
+
+def test_same_seed_same_weights_as_reference():
+    from differential_equations_dnn_b200 import neural_networks as nn_, dgm_net
+    cases = {"heat_dgm_h128l3": lambda: dgm_net.DGM(2, 1, 128, 3),
+             "heat_mlp_relu_h128l3": lambda: nn_.MLP(2, 1, 128, 3),
+             "heat_mlp_sigmoid_h50l1": lambda: nn_.MLP(2, 1, 50, 1, activation="sigmoid"),
+             "heat_mlp_leaky_h32l2": lambda: nn_.MLP(2, 1, 32, 2, activation="leaky_relu"),
+             "fhn_mlp_tanh_h128l3": lambda: nn_.MLP(1, 2, 128, 3, activation="tanh"),
+             "fredholm_dgmraw_h32l1_k50": lambda: nn_.DGM(1, 1, 32, 1)}
+    for name, ctor in cases.items():
+        torch.manual_seed(1234)
+        net = ctor()
+        assert np.array_equal(net.flat_theta().numpy(), golden(name)["theta"]), name
+
+
+def test_module_contract_cpu():
+    from differential_equations_dnn_b200 import neural_networks as nn_, dgm_net
+    net = nn_.DGM(input_dim=1, output_dim=1, hidden_size=32)
+    names = [n for n, _ in net.named_parameters()]
+    assert names[:3] == ["x_in.weight", "x_in.bias", "dgm1.Uz"] and names[-1] == "x_out.bias"
+    assert tuple(net.layers[0].Uz.shape) == (1, 32) and tuple(net.layers[0].bz.shape) == (1, 32)
+    assert int(net.live_mask().sum()) == 4449 and net.flat_theta().numel() == 8801
+    # parameters are views of one buffer, and stay so after dtype/device style conversions
+    f = net.flat_theta()
+    with torch.no_grad():
+        net.x_out.bias.fill_(3.0)
+    assert f[-1].item() == 3.0
+    net = net.float()
+    f2 = net.flat_theta()
+    with torch.no_grad():
+        net.x_in.weight.zero_()
+    assert f2[:32].abs().sum().item() == 0
+    m = dgm_net.DGM(2, 1, 128, 3)
+    assert m.flat_theta().numel() == 201729
+    assert [k for k in m.state_dict()][2] == "layers.0.Z_wg.weight"
+    with pytest.raises(NotImplementedError):
+        nn_.MLP(batch_norm=True)
+    with pytest.raises(Exception, match="no CPU"):
+        m(torch.zeros(4, 2))
+
+
+def test_fused_adam_binds_to_flat_buffer():
+    from differential_equations_dnn_b200 import dgm_net
+    from differential_equations_dnn_b200.optim import FusedAdam
+    net = dgm_net.DGM(1, 1, 8, 1)
+    opt = FusedAdam(net.parameters(), lr=1e-4)
+    assert opt.param_groups[0]["lr"] == 1e-4 and opt.net is net
+    with pytest.raises(ValueError):
+        FusedAdam([torch.nn.Parameter(torch.zeros(3))])
+
+
+def test_search_space_and_trials():
+    from differential_equations_dnn_b200 import parallel
+    cfgs = parallel.sample_search_space(10, seed=0)
+    assert len(cfgs) == 10 and all(1 <= c["batch_size"] < 512 and 1000 <= c["n_iters"] < 50000
+                                   and 1e-4 <= c["lrate"] <= 1e-1 for c in cfgs)
+    res = parallel.run_trials(lambda c: c["lrate"], cfgs)
+    assert parallel.best_trial(res)["loss"] == min(c["lrate"] for c in cfgs)
