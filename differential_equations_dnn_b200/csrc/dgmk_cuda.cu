@@ -30,6 +30,17 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
   out[i] += (float)s;
 }
 
+// out[r * ldo + c] += sum_s part[s][r][c]  (r < rows, c < cols): strided variant
+__global__ void __launch_bounds__(256) reduce_partials_2d_kernel(const float* __restrict__ part, int nparts, int rows,
+                                                                 int cols, float* __restrict__ out, int64_t ldo) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  double s = 0.0;
+  for (int p = 0; p < nparts; ++p) s += (double)part[(int64_t)p * rows * cols + i];
+  int r = i / cols, c = i - r * cols;
+  out[(int64_t)r * ldo + c] += (float)s;
+}
+
 // out-partials[blk][e][n] = sum_{r in block's row strip} Wt[r][e] * Mat[r][n]
 // grid = (ceil(N / 128), nblk); thread = one column n, 4 weighted sums.
 template <bool WEIGHTED>
@@ -143,11 +154,13 @@ struct CudaBackend {
     reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, nparts, n, out);
     post();
   }
+  // out[N,Kd] += A^T S ; if E: outE[e * ldoE + n] += sum_m A[m,n] E[m,e]  (fused in the same pass)
   void gemm_tn_acc(const float* A, int64_t lda, const float* S, int64_t lds, float* out, int N, int Kd, int64_t M,
-                   float* part, int64_t part_n) {
+                   const float* E, float* outE, int64_t ldoE, float* part, int64_t part_n) {
     if (M <= 0) return;
     const int64_t tile = (int64_t)N * Kd;
-    int64_t max_splits = part_n / tile;
+    const int64_t per_split = tile + (E ? 4 * (int64_t)N : 0);
+    int64_t max_splits = part_n / per_split;
     if (max_splits > 256) max_splits = 256;
     if (max_splits < 1) { if (!err) err = "internal: partial buffer too small"; return; }
     // aim for >= 4 waves of CTAs, at least 1024 rows per split, at most max_splits
@@ -160,12 +173,17 @@ struct CudaBackend {
     if (splits < 1) splits = 1;
     int64_t rps = ((M + splits - 1) / splits + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
     splits = (M + rps - 1) / rps;
+    float* PE = E ? part + splits * tile : nullptr;
     dim3 grid(Kd / BN, (N + GEMM_BM - 1) / GEMM_BM, (unsigned)splits);
-    if (BN == 128) gemm_tn_kernel<128><<<grid, GEMM_NT, 0, st>>>(A, lda, S, lds, part, N, Kd, M, rps);
-    else if (BN == 64) gemm_tn_kernel<64><<<grid, GEMM_NT, 0, st>>>(A, lda, S, lds, part, N, Kd, M, rps);
-    else gemm_tn_kernel<32><<<grid, GEMM_NT, 0, st>>>(A, lda, S, lds, part, N, Kd, M, rps);
+    if (BN == 128) gemm_tn_kernel<128><<<grid, GEMM_NT, 0, st>>>(A, lda, S, lds, part, N, Kd, M, rps, E, PE);
+    else if (BN == 64) gemm_tn_kernel<64><<<grid, GEMM_NT, 0, st>>>(A, lda, S, lds, part, N, Kd, M, rps, E, PE);
+    else gemm_tn_kernel<32><<<grid, GEMM_NT, 0, st>>>(A, lda, S, lds, part, N, Kd, M, rps, E, PE);
     post();
     reduce(part, (int)splits, tile, out);
+    if (E) {
+      reduce_partials_2d_kernel<<<(unsigned)((4 * N + 255) / 256), 256, 0, st>>>(PE, (int)splits, 4, N, outE, ldoE);
+      post();
+    }
   }
   void wcolsum_acc(const float* Mat, int64_t ldm, int N, const float* Wt, int64_t M, float* out, float* part,
                    int64_t part_n) {

@@ -7,6 +7,7 @@
 //
 //   gemm_nn : C[M,N] (+)= A[M,K] * B[K,N]        forward / data-gradient
 //   gemm_tn : P[s][N,Kd]  = sum_{m in split s} A[m,N]^T * S[m,Kd]   weight-gradient
+//             (+ PE[s][4,N] = A^T E for the input-map / bias gradients, fused)
 //
 // All operands row-major.  K, N multiples of 32 (hidden sizes are padded to
 // 32), M arbitrary.  128 x BN CTA tile, 256 threads, 8 x (BN/16) register
@@ -32,28 +33,36 @@ struct GemmTile {
 };
 
 // ---- inner product on one k-slice ------------------------------------------
+// Packed FP32 FMA (fma.rn.f32x2 -> SASS FFMA2, sm_100+): the accumulators are column
+// pairs, b comes as natural float2 pairs out of the float4 shared loads and a[i] is the
+// scalar-broadcast operand (ptxas folds make_float2(a,a) into the .F32 operand form, no
+// MOV).  Same IEEE fma per lane as FFMA; half the issue slots, which leaves room for the
+// LDS / address instructions next to a saturated FMA pipe (profiles/r01_notes.md).
 template <int BN>
 __device__ __forceinline__ void mma_slice(const float (*As)[GEMM_BM + GEMM_APAD],
                                           const float (*Bs)[BN], int tx, int ty,
-                                          float (&acc)[8][GemmTile<BN>::TN]) {
+                                          float2 (&acc)[8][GemmTile<BN>::TN / 2]) {
   constexpr int TN = GemmTile<BN>::TN;
 #pragma unroll
   for (int kk = 0; kk < GEMM_BK; ++kk) {
-    float a[8], b[TN];
+    float a[8];
+    float2 b[TN / 2];
     *reinterpret_cast<float4*>(&a[0]) = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
     *reinterpret_cast<float4*>(&a[4]) = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
     if constexpr (TN == 8) {
       *reinterpret_cast<float4*>(&b[0]) = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      *reinterpret_cast<float4*>(&b[4]) = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+      *reinterpret_cast<float4*>(&b[2]) = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
     } else if constexpr (TN == 4) {
       *reinterpret_cast<float4*>(&b[0]) = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
     } else {
-      *reinterpret_cast<float2*>(&b[0]) = *reinterpret_cast<const float2*>(&Bs[kk][tx * 2]);
+      b[0] = *reinterpret_cast<const float2*>(&Bs[kk][tx * 2]);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 8; ++i) {
+      const float2 a2 = make_float2(a[i], a[i]);
 #pragma unroll
-      for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      for (int j = 0; j < TN / 2; ++j) acc[i][j] = __ffma2_rn(a2, b[j], acc[i][j]);
+    }
   }
 }
 
@@ -82,11 +91,11 @@ gemm_nn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
   const int64_t m0 = (int64_t)blockIdx.y * GEMM_BM;
   const int n0 = blockIdx.x * BN;
 
-  float acc[8][T::TN];
+  float2 acc[8][T::TN / 2];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < T::TN; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < T::TN / 2; ++j) acc[i][j] = make_float2(0.f, 0.f);
 
   float4 ra[2], rb[T::B_PER_T];
   auto load_g = [&](int k0) {
@@ -150,18 +159,18 @@ gemm_nn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         float4* p = reinterpret_cast<float4*>(crow + h * 64 + tx * 4);
-        float4 v = make_float4(acc[i][h * 4 + 0], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]);
+        float4 v = make_float4(acc[i][h * 2].x, acc[i][h * 2].y, acc[i][h * 2 + 1].x, acc[i][h * 2 + 1].y);
         if constexpr (ACCUM) { float4 o = *p; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
         *p = v;
       }
     } else if constexpr (T::TN == 4) {
       float4* p = reinterpret_cast<float4*>(crow + tx * 4);
-      float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      float4 v = make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y);
       if constexpr (ACCUM) { float4 o = *p; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
       *p = v;
     } else {
       float2* p = reinterpret_cast<float2*>(crow + tx * 2);
-      float2 v = make_float2(acc[i][0], acc[i][1]);
+      float2 v = acc[i][0];
       if constexpr (ACCUM) { float2 o = *p; v.x += o.x; v.y += o.y; }
       *p = v;
     }
@@ -171,10 +180,15 @@ gemm_nn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
 // ---- P[z][N,Kd] = sum_{m in [z*rows_per_split, ...)} A[m, 0:N]^T S[m, 0:Kd] ---------
 // grid = (Kd / BN, ceil(N / 128), splits).  Partials are reduced in a fixed order
 // by reduce_partials (deterministic, FP64 accumulate): SURVEY 7.3 H4.
+// When E != nullptr the CTAs of the first column tile also accumulate
+//   PE[z][e][n] = sum_m A[m, n] * E[m, e]   (e < 4)
+// from the A slices they already stage in shared memory: that is grad[U | b] = Abar^T E
+// (SURVEY 7.1 "input map"), which a separate pass would have to re-read Abar for.
 template <int BN>
 __global__ void __launch_bounds__(GEMM_NT, 2)
 gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ S, int64_t lds,
-               float* __restrict__ P, int N, int Kd, int64_t M, int64_t rows_per_split) {
+               float* __restrict__ P, int N, int Kd, int64_t M, int64_t rows_per_split,
+               const float* __restrict__ E, float* __restrict__ PE) {
   using T = GemmTile<BN>;
   __shared__ __align__(16) float As[2][GEMM_BK][GEMM_BM + GEMM_APAD];
   __shared__ __align__(16) float Bs[2][GEMM_BK][BN];
@@ -183,15 +197,24 @@ gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
   const int j0 = blockIdx.x * BN;       // output col (column of S)
   const int64_t mb = (int64_t)blockIdx.z * rows_per_split;
   const int64_t me = (mb + rows_per_split < M) ? mb + rows_per_split : M;
+  const bool do_e = (E != nullptr) && (blockIdx.x == 0);
+  __shared__ __align__(16) float Es[2][GEMM_BK][4];
+  float4 re = make_float4(0.f, 0.f, 0.f, 0.f);
+  float eacc0 = 0.f, eacc1 = 0.f;
+  const int ei = tid & 127, eh = (tid >> 7) * 2;
 
-  float acc[8][T::TN];
+  float2 acc[8][T::TN / 2];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < T::TN; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < T::TN / 2; ++j) acc[i][j] = make_float2(0.f, 0.f);
 
   float4 ra[2], rb[T::B_PER_T];
   auto load_g = [&](int64_t mm0) {
+    if (do_e && tid < GEMM_BK) {
+      int64_t m = mm0 + tid;
+      re = (m < me) ? __ldg(reinterpret_cast<const float4*>(E) + m) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {  // 16 rows x 128 cols = 512 float4
       int idx = tid + q * GEMM_NT;
@@ -213,6 +236,7 @@ gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
     }
   };
   auto store_s = [&](int buf) {
+    if (do_e && tid < GEMM_BK) *reinterpret_cast<float4*>(&Es[buf][tid][0]) = re;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       int idx = tid + q * GEMM_NT;
@@ -238,11 +262,24 @@ gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
       const int buf = (int)(kt & 1);
       if (kt + 1 < nk) load_g(mb + (kt + 1) * GEMM_BK);
       mma_slice<BN>(As[buf], Bs[buf], tx, ty, acc);
+      if (do_e) {
+#pragma unroll
+        for (int mm = 0; mm < GEMM_BK; ++mm) {
+          const float av = As[buf][mm][ei];
+          eacc0 = fmaf(av, Es[buf][mm][eh], eacc0);
+          eacc1 = fmaf(av, Es[buf][mm][eh + 1], eacc1);
+        }
+      }
       if (kt + 1 < nk) {
         store_s(buf ^ 1);
         __syncthreads();
       }
     }
+  }
+  if (do_e && i0 + ei < N) {
+    float* pe = PE + (int64_t)blockIdx.z * 4 * N;
+    pe[(int64_t)eh * N + i0 + ei] = eacc0;
+    pe[(int64_t)(eh + 1) * N + i0 + ei] = eacc1;
   }
   float* Pz = P + (int64_t)blockIdx.z * N * Kd;
 #pragma unroll
@@ -250,7 +287,8 @@ gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
     int r = i0 + row_of(ty, i);
     if (r >= N) continue;
 #pragma unroll
-    for (int j = 0; j < T::TN; ++j) Pz[(int64_t)r * Kd + j0 + col_of<BN>(tx, j)] = acc[i][j];
+    for (int j = 0; j < T::TN; ++j)
+      Pz[(int64_t)r * Kd + j0 + col_of<BN>(tx, j)] = (j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x;
   }
 }
 

@@ -59,7 +59,7 @@ inline int64_t rev_floats_per_row(const NetDims& n, int C) {
 constexpr int64_t PART_FLOATS_MIN = 1 << 20;
 inline int64_t part_floats(const NetDims& n) {
   // gemm_tn partials: <= 256 splits x [3Hp, Hp]; wcolsum partials: <= 512 blocks x 4 x 4Hp
-  int64_t a = 256LL * 3 * n.Hp * n.Hp, b = 512LL * 4 * 4 * n.Hp;
+  int64_t a = 256LL * (3 * n.Hp * n.Hp + 4 * 3 * n.Hp), b = 512LL * 4 * 4 * n.Hp;
   int64_t m = a > b ? a : b;
   return m > PART_FLOATS_MIN ? m : PART_FLOATS_MIN;
 }
@@ -217,8 +217,8 @@ struct Pipeline {
             MlpRevFn<CS, ACT> f; f.G = pb.G[l]; f.YB = SBn; f.AB = rb.AB; f.Hp = Hp;
             bk.ew(f, R * Hp);
           })
-          bk.gemm_tn_acc(rb.AB, Hp, pb.S[l], Hp, Gp + c.pl.g_w[l], Hp, Hp, M, c.part, c.part_n);
-          bk.wcolsum_acc(rb.AB, Hp, Hp, pb.E, M, Gp + c.pl.g_ub[l], c.part, c.part_n);
+          // grad W = Abar^T Y_prev, and grad b (row 2 of Abar^T E) in the same pass
+          bk.gemm_tn_acc(rb.AB, Hp, pb.S[l], Hp, Gp + c.pl.g_w[l], Hp, Hp, M, pb.E, Gp + c.pl.g_ub[l], Hp, c.part, c.part_n);
           bk.gemm_nn(rb.AB, Hp, c.Wp + c.pl.wb[l], Hp, SBp, Hp, M, Hp, Hp, false);
         } else {
           DGMK_GACT_SWITCH(n.gate_act(), ACT, {
@@ -234,9 +234,11 @@ struct Pipeline {
           // s bar += [abar_Z | abar_G | abar_R] [W_z; W_g; W_r]
           bk.gemm_nn(rb.AB, 4 * Hp, c.Wp + c.pl.wb[l], Hp, SBp, Hp, M, Hp, 3 * Hp, true);
           // weight gradients
-          bk.gemm_tn_acc(rb.AB, 4 * Hp, pb.S[l], Hp, Gp + c.pl.g_w[l], 3 * Hp, Hp, M, c.part, c.part_n);
-          bk.gemm_tn_acc(rb.AB + 3 * Hp, 4 * Hp, pb.SR[l], Hp, Gp + c.pl.g_w[l] + (int64_t)3 * Hp * Hp, Hp, Hp, M, c.part, c.part_n);
-          bk.wcolsum_acc(rb.AB, 4 * Hp, 4 * Hp, pb.E, M, Gp + c.pl.g_ub[l], c.part, c.part_n);
+          // weight gradients; grad[U | b] = Abar^T E rides along in the same passes
+          bk.gemm_tn_acc(rb.AB, 4 * Hp, pb.S[l], Hp, Gp + c.pl.g_w[l], 3 * Hp, Hp, M, pb.E, Gp + c.pl.g_ub[l], 4 * Hp,
+                         c.part, c.part_n);
+          bk.gemm_tn_acc(rb.AB + 3 * Hp, 4 * Hp, pb.SR[l], Hp, Gp + c.pl.g_w[l] + (int64_t)3 * Hp * Hp, Hp, Hp, M, pb.E,
+                         Gp + c.pl.g_ub[l] + 3 * Hp, 4 * Hp, c.part, c.part_n);
         }
         float* t = SBn; SBn = SBp; SBp = t;
       }

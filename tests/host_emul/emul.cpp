@@ -21,14 +21,17 @@ struct HostBackend {
         C[m * ldc + n] = acc ? C[m * ldc + n] + s : s;
       }
   }
-  void gemm_tn_acc(const float* A, int64_t lda, const float* S, int64_t lds, float* out, int N, int Kd, int64_t M, float*, int64_t) {
-    std::vector<double> acc((size_t)N * Kd, 0.0);
+  void gemm_tn_acc(const float* A, int64_t lda, const float* S, int64_t lds, float* out, int N, int Kd, int64_t M,
+                   const float* E, float* outE, int64_t ldoE, float*, int64_t) {
+    std::vector<double> acc((size_t)N * Kd, 0.0), eacc((size_t)4 * N, 0.0);
     for (int64_t m = 0; m < M; ++m)
       for (int n = 0; n < N; ++n) {
         double a = A[m * lda + n];
         for (int k = 0; k < Kd; ++k) acc[(size_t)n * Kd + k] += a * S[m * lds + k];
+        if (E) for (int e = 0; e < 4; ++e) eacc[(size_t)e * N + n] += a * E[m * 4 + e];
       }
     for (size_t i = 0; i < acc.size(); ++i) out[i] += (float)acc[i];
+    if (E) for (int e = 0; e < 4; ++e) for (int n = 0; n < N; ++n) outE[e * ldoE + n] += (float)eacc[(size_t)e * N + n];
   }
   void wcolsum_acc(const float* Mat, int64_t ldm, int N, const float* Wt, int64_t M, float* out, float*, int64_t) {
     int NE = Wt ? 4 : 1;

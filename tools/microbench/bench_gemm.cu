@@ -150,9 +150,9 @@ int main() {
       CK(cudaMalloc(&P, (size_t)splits * N * Kd * 4)); CK(cudaMalloc(&G, N * Kd * 4)); CK(cudaMalloc(&Gr, N * Kd * 4));
       int BNt = (Kd % 128 == 0) ? 128 : (Kd % 64 == 0) ? 64 : 32;
       dim3 g2(Kd / BNt, (N + 127) / 128, splits);
-      if (BNt == 128) dgmk::gemm_tn_kernel<128><<<g2, 256>>>(Cr, ldc, A, lda, P, N, Kd, c.M, rps);
-      else if (BNt == 64) dgmk::gemm_tn_kernel<64><<<g2, 256>>>(Cr, ldc, A, lda, P, N, Kd, c.M, rps);
-      else dgmk::gemm_tn_kernel<32><<<g2, 256>>>(Cr, ldc, A, lda, P, N, Kd, c.M, rps);
+      if (BNt == 128) dgmk::gemm_tn_kernel<128><<<g2, 256>>>(Cr, ldc, A, lda, P, N, Kd, c.M, rps, nullptr, nullptr);
+      else if (BNt == 64) dgmk::gemm_tn_kernel<64><<<g2, 256>>>(Cr, ldc, A, lda, P, N, Kd, c.M, rps, nullptr, nullptr);
+      else dgmk::gemm_tn_kernel<32><<<g2, 256>>>(Cr, ldc, A, lda, P, N, Kd, c.M, rps, nullptr, nullptr);
       sum_parts<<<(N * Kd + 255) / 256, 256>>>(P, splits, N * Kd, G);
       naive_tn<<<(N * Kd + 255) / 256, 256>>>(Cr, ldc, A, lda, Gr, N, Kd, c.M);
       CK(cudaDeviceSynchronize());
@@ -184,7 +184,7 @@ int main() {
       printf("%s: %.3f ms  %.2f TFLOP/s\n", t.name, ms, 2.0 * M * t.N * t.K / ms * 1e-9);
     }
     dim3 g2(1, 3, splits);
-    float ms = time_ms([&] { dgmk::gemm_tn_kernel<128><<<g2, 256>>>(C, 512, A, 512, P, 384, 128, M, rps); }, 10);
+    float ms = time_ms([&] { dgmk::gemm_tn_kernel<128><<<g2, 256>>>(C, 512, A, 512, P, 384, 128, M, rps, nullptr, nullptr); }, 10);
     printf("wgrad ZGR [M,384]^T x [M,128]: %.3f ms  %.2f TFLOP/s\n", ms, 2.0 * M * 384 * 128 / ms * 1e-9);
     CK(cudaGetLastError());
   }
