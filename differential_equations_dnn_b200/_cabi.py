@@ -61,6 +61,8 @@ _CUDA_ONLY = {
     "dgmk_launch_count": (C.c_ulonglong, []),
     "dgmk_ffma_probe": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
     "dgmk_gemm_probe": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int64, _P]),
+    "dgmk_gemm_tc_probe": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int64, _P]),
+    "dgmk_set_gemm_engine": (None, [C.c_int]),
 }
 EXPORTS = tuple(_SIGNATURES) + tuple(_CUDA_ONLY)
 

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include "dgmk_capi_impl.h"
 #include "dgmk_gemm.cuh"
+#include "dgmk_gemm_tc.cuh"
 
 namespace dgmk {
 
@@ -13,6 +14,8 @@ constexpr int EW_THREADS = 256;
 // number of kernels this library has launched in this process (diagnostic: bench.py
 // reports it as gpu_launches)
 static unsigned long long g_launches = 0;
+// GEMM engine selector for A/B measurements (dgmk_set_gemm_engine): tensor cores on by default
+static bool g_use_tc = true;
 
 template <class F>
 __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const F f, int64_t n) {
@@ -119,7 +122,9 @@ struct CudaBackend {
   cudaStream_t st;
   const char* err;
   int sms;
-  explicit CudaBackend(void* stream) : st((cudaStream_t)stream), err(nullptr), sms(148) {
+  bool use_tc;
+  int64_t hl_stride = 0;  // distance between the plain / tf32-hi / tf32-lo copies of the packed weights
+  explicit CudaBackend(void* stream) : st((cudaStream_t)stream), err(nullptr), sms(148), use_tc(g_use_tc) {
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) {
       int v = 0;
@@ -138,9 +143,25 @@ struct CudaBackend {
     ew_kernel<F><<<(unsigned)blocks, EW_THREADS, 0, st>>>(f, n);
     post();
   }
-  void gemm_nn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M, int N, int K,
-               bool acc) {
+  // C[M,N] (+)= A[M,K] B[K,N].  Shapes the tcgen05 tile covers (N % 128 == 0, K % 32 == 0, i.e.
+  // hidden sizes that are multiples of 128) run on the tensor cores with 3xTF32 split
+  // accumulation; everything else runs on the FP32 FFMA2 tile.
+  void gemm_nn(const float* A, int64_t lda, const float* B, int64_t ldb, const float* Bt, int64_t ldbt, float* C,
+               int64_t ldc, int64_t M, int N, int K, bool acc) {
     if (M <= 0) return;
+    if (use_tc && N % tc::BN == 0 && K % tc::KC == 0) {
+      static bool attr_done = false;
+      if (!attr_done) {
+        note(cudaFuncSetAttribute(tc::gemm_nn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        note(cudaFuncSetAttribute(tc::gemm_nn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        attr_done = true;
+      }
+      dim3 grid(N / tc::BN, (unsigned)((M + tc::BM - 1) / tc::BM));
+      if (acc) tc::gemm_nn_tc_kernel<true><<<grid, tc::NT, tc::SMEM_BYTES, st>>>(A, lda, Bt, ldbt, hl_stride, C, ldc, M, K);
+      else tc::gemm_nn_tc_kernel<false><<<grid, tc::NT, tc::SMEM_BYTES, st>>>(A, lda, Bt, ldbt, hl_stride, C, ldc, M, K);
+      post();
+      return;
+    }
     const int BN = (N % 128 == 0) ? 128 : (N % 64 == 0) ? 64 : 32;
     dim3 grid(N / BN, (unsigned)((M + GEMM_BM - 1) / GEMM_BM));
 #define DGMK_NN(bn)                                                                                   \
@@ -252,6 +273,17 @@ __global__ void __launch_bounds__(256) ffma_probe_kernel(float* out, const float
 
 extern "C" {
 unsigned long long dgmk_launch_count(void) { return dgmk::g_launches; }
+// 0 = FP32 FFMA2 tiles only, 1 = tcgen05 3xTF32 tiles where the shape allows (default)
+void dgmk_set_gemm_engine(int tensor_cores) { dgmk::g_use_tc = tensor_cores != 0; }
+// same tcgen05 tile the pipeline launches: C[M,N] = A[M,K] Bt[N,K]^T, lda = ldc = ld
+int dgmk_gemm_tc_probe(const float* A, const float* Bt, float* C, int64_t M, int N, int K, int64_t ld, void* stream) {
+  if (N % 128 || K % 32) return DGMK_EINVAL;
+  dgmk::CudaBackend bk(stream);
+  bk.use_tc = true;
+  bk.hl_stride = (int64_t)N * K;  // Bt = [plain | tf32-hi | tf32-lo], each N*K floats
+  bk.gemm_nn(A, ld, nullptr, 0, Bt, K, C, ld, M, N, K, false);
+  return bk.error() ? DGMK_ECUDA : 0;
+}
 // FP32 FFMA peak probe: launches blocks x 256 threads, each doing 64*iters FFMAs.
 // `in` >= 32 floats, `out` >= blocks*256 floats (device).  flops = 2*64*iters*256*blocks.
 int dgmk_ffma_probe(const float* in, float* out, int blocks, int iters, void* stream) {
@@ -263,7 +295,8 @@ int dgmk_ffma_probe(const float* in, float* out, int blocks, int iters, void* st
 int dgmk_gemm_probe(const float* A, const float* B, float* C, int64_t M, int N, int K, int64_t ld, void* stream) {
   if (N % 32 || K % 16) return DGMK_EINVAL;
   dgmk::CudaBackend bk(stream);
-  bk.gemm_nn(A, ld, B, N, C, ld, M, N, K, false);
+  bk.use_tc = false;  // the FFMA2 tile; B is [K,N]
+  bk.gemm_nn(A, ld, B, N, nullptr, 0, C, ld, M, N, K, false);
   return bk.error() ? DGMK_ECUDA : 0;
 }
 }

@@ -48,6 +48,20 @@ DGMK_HD int cs_ndirs(int cs) {
   return cs == CS_V ? 0 : (cs == CS_D1O1 || cs == CS_D1O2) ? 1 : 2;
 }
 
+// tf32 split used by the tensor-core GEMM tiles: hi = x rounded to 10 explicit mantissa
+// bits (nearest, ties away -- cvt.rna.tf32.f32), lo = x - hi (exact in FP32)
+DGMK_HD float tf32_round(float x) {
+#if defined(__CUDA_ARCH__)
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+#else
+  union { float f; uint32_t u; } v; v.f = x;
+  v.u = (v.u + 0x1000u) & 0xFFFFE000u;
+  return v.f;
+#endif
+}
+
 // ---- activations ------------------------------------------------------------
 // tanhf/expf are the accurate libm-grade device routines (no --use_fast_math):
 // MUFU.TANH's 2^-11 relative error would break the 1e-5 gradient parity

@@ -32,17 +32,24 @@ struct XSrc {
 };
 
 // ---- parameter packing --------------------------------------------------------
+// packed = [plain | tf32-hi | tf32-lo], three copies of the same layout hl apart
 struct PackFn {
-  SegTable t; const float* theta; float* packed;
+  SegTable t; const float* theta; float* packed; int64_t hl;
   DGMK_HD void operator()(int64_t i) const {
     for (int s = 0; s < t.n; ++s) {
       const Seg& g = t.s[s];
       int32_t k = (int32_t)i - g.theta_off;
       if (k >= 0 && k < g.n) {
         int r = k / g.cols, c = k - r * g.cols;
-        float v = theta[i];
-        if (g.a_off >= 0) packed[g.a_off + (int64_t)r * g.a_rs + (int64_t)c * g.a_cs] = v;
-        if (g.b_off >= 0) packed[g.b_off + (int64_t)r * g.b_rs + (int64_t)c * g.b_cs] = v;
+        const float v = theta[i], hi = tf32_round(v), lo = v - hi;
+        if (g.a_off >= 0) {
+          const int64_t o = g.a_off + (int64_t)r * g.a_rs + (int64_t)c * g.a_cs;
+          packed[o] = v; packed[o + hl] = hi; packed[o + 2 * hl] = lo;
+        }
+        if (g.b_off >= 0) {
+          const int64_t o = g.b_off + (int64_t)r * g.b_rs + (int64_t)c * g.b_cs;
+          packed[o] = v; packed[o + hl] = hi; packed[o + 2 * hl] = lo;
+        }
         return;
       }
     }

@@ -2,6 +2,9 @@
 // every layer, a-form stash in HBM), reverse pass (adjoint of the jet program),
 // weight-gradient contractions, and the four fused training steps.
 //
+// gemm_nn(A, lda, B, ldb, Bt, ldbt, C, ...) receives the weight operand in BOTH packed
+// orientations (B = [K,N] for the FFMA tile, Bt = [N,K] K-major for the tcgen05 tile).
+//
 // Templated on a backend that provides the heavy primitives (GEMM tiles, element-
 // wise launches, reductions).  The product backend is CUDA (dgmk_cuda.cu); the
 // test-only host harness (tests/host_emul) instantiates the same orchestration with
@@ -105,7 +108,7 @@ inline size_t rev_bytes(const NetDims& n, int64_t Mmax) {
   return b;
 }
 inline bool carve_ctx(Carver& cv, Ctx* c, int64_t max_points) {
-  c->Wp = cv.take(c->pl.w_total);
+  c->Wp = cv.take(c->pl.w_total * 3);  // plain | tf32-hi | tf32-lo
   c->Gp = cv.take(c->pl.g_total);
   c->part_n = part_floats(c->n);
   c->part = cv.take(c->part_n);
@@ -113,7 +116,7 @@ inline bool carve_ctx(Carver& cv, Ctx* c, int64_t max_points) {
   return cv.ok;
 }
 inline size_t ctx_bytes(const NetDims& n, const PackedLayout& pl, int64_t max_points) {
-  return carve_bytes(pl.w_total) + carve_bytes(pl.g_total) + carve_bytes(part_floats(n)) + carve_bytes(max_points);
+  return carve_bytes(pl.w_total * 3) + carve_bytes(pl.g_total) + carve_bytes(part_floats(n)) + carve_bytes(max_points);
 }
 
 // ---- dispatch helpers --------------------------------------------------------------
@@ -147,8 +150,9 @@ struct Pipeline {
   const F4* ub(int l) const { return (const F4*)(c.Wp + c.pl.ub[l]); }
 
   void pack(const float* theta) {
-    bk.zero(c.Wp, (size_t)c.pl.w_total * 4);
-    PackFn f; f.t = c.pack; f.theta = theta; f.packed = c.Wp;
+    bk.zero(c.Wp, (size_t)c.pl.w_total * 4 * 3);
+    PackFn f; f.t = c.pack; f.theta = theta; f.packed = c.Wp; f.hl = c.pl.w_total;
+    bk.hl_stride = c.pl.w_total;
     bk.ew(f, num_params(c.n));
   }
   void zero_grads() { bk.zero(c.Gp, (size_t)c.pl.g_total * 4); }
@@ -172,18 +176,19 @@ struct Pipeline {
       })
       for (int l = 0; l < n.L; ++l) {
         if (!n.is_dgm()) {
-          bk.gemm_nn(pb.S[l], Hp, c.Wp + c.pl.wf[l], Hp, pb.G[l], Hp, M, Hp, Hp, false);
+          bk.gemm_nn(pb.S[l], Hp, c.Wp + c.pl.wf[l], Hp, c.Wp + c.pl.wb[l], Hp, pb.G[l], Hp, M, Hp, Hp, false);
           DGMK_ACT_SWITCH(n.act, ACT, {
             MlpActFn<CS, ACT> f; f.G = pb.G[l]; f.ub = ub(l); f.Yn = pb.S[l + 1]; f.Hp = Hp;
             bk.ew(f, R * Hp);
           })
         } else {
-          bk.gemm_nn(pb.S[l], Hp, c.Wp + c.pl.wf[l], 3 * Hp, pb.G[l], 4 * Hp, M, 3 * Hp, Hp, false);
+          bk.gemm_nn(pb.S[l], Hp, c.Wp + c.pl.wf[l], 3 * Hp, c.Wp + c.pl.wb[l], Hp, pb.G[l], 4 * Hp, M, 3 * Hp, Hp, false);
           DGMK_GACT_SWITCH(n.gate_act(), ACT, {
             DgmFwd1Fn<CS, ACT> f; f.xs = pb.xs; f.A4 = pb.G[l]; f.ub = ub(l); f.S = pb.S[l]; f.SR = pb.SR[l]; f.Hp = Hp;
             bk.ew(f, R * Hp);
           })
-          bk.gemm_nn(pb.SR[l], Hp, c.Wp + c.pl.wfh[l], Hp, pb.G[l] + 3 * Hp, 4 * Hp, M, Hp, Hp, false);
+          bk.gemm_nn(pb.SR[l], Hp, c.Wp + c.pl.wfh[l], Hp, c.Wp + c.pl.wb[l] + (int64_t)3 * Hp * Hp, Hp, pb.G[l] + 3 * Hp, 4 * Hp, M, Hp, Hp,
+                     false);
           DGMK_GACT_SWITCH(n.gate_act(), ACT, {
             DgmFwd2Fn<CS, ACT> f; f.xs = pb.xs; f.A4 = pb.G[l]; f.ub = ub(l); f.S = pb.S[l]; f.Sn = pb.S[l + 1]; f.Hp = Hp;
             bk.ew(f, R * Hp);
@@ -219,20 +224,21 @@ struct Pipeline {
           })
           // grad W = Abar^T Y_prev, and grad b (row 2 of Abar^T E) in the same pass
           bk.gemm_tn_acc(rb.AB, Hp, pb.S[l], Hp, Gp + c.pl.g_w[l], Hp, Hp, M, pb.E, Gp + c.pl.g_ub[l], Hp, c.part, c.part_n);
-          bk.gemm_nn(rb.AB, Hp, c.Wp + c.pl.wb[l], Hp, SBp, Hp, M, Hp, Hp, false);
+          bk.gemm_nn(rb.AB, Hp, c.Wp + c.pl.wb[l], Hp, c.Wp + c.pl.wf[l], Hp, SBp, Hp, M, Hp, Hp, false);
         } else {
           DGMK_GACT_SWITCH(n.gate_act(), ACT, {
             DgmRev1Fn<CS, ACT> f; f.A4 = pb.G[l]; f.S = pb.S[l]; f.SBn = SBn; f.AB4 = rb.AB; f.SBp = SBp; f.Hp = Hp;
             bk.ew(f, R * Hp);
           })
           // (s*R)bar = abar_H W_h
-          bk.gemm_nn(rb.AB + 3 * Hp, 4 * Hp, c.Wp + c.pl.wb[l] + (int64_t)3 * Hp * Hp, Hp, rb.SRB, Hp, M, Hp, Hp, false);
+          bk.gemm_nn(rb.AB + 3 * Hp, 4 * Hp, c.Wp + c.pl.wb[l] + (int64_t)3 * Hp * Hp, Hp, c.Wp + c.pl.wfh[l], Hp, rb.SRB, Hp, M, Hp,
+                     Hp, false);
           DGMK_GACT_SWITCH(n.gate_act(), ACT, {
             DgmRev2Fn<CS, ACT> f; f.A4 = pb.G[l]; f.S = pb.S[l]; f.SRB = rb.SRB; f.AB4 = rb.AB; f.SBp = SBp; f.Hp = Hp;
             bk.ew(f, R * Hp);
           })
           // s bar += [abar_Z | abar_G | abar_R] [W_z; W_g; W_r]
-          bk.gemm_nn(rb.AB, 4 * Hp, c.Wp + c.pl.wb[l], Hp, SBp, Hp, M, Hp, 3 * Hp, true);
+          bk.gemm_nn(rb.AB, 4 * Hp, c.Wp + c.pl.wb[l], Hp, c.Wp + c.pl.wf[l], 3 * Hp, SBp, Hp, M, Hp, 3 * Hp, true);
           // weight gradients
           // weight gradients; grad[U | b] = Abar^T E rides along in the same passes
           bk.gemm_tn_acc(rb.AB, 4 * Hp, pb.S[l], Hp, Gp + c.pl.g_w[l], 3 * Hp, Hp, M, pb.E, Gp + c.pl.g_ub[l], 4 * Hp,

@@ -130,6 +130,10 @@ int dgmk_adam(float* theta, float* m, float* v, const float* grad, const uint8_t
 /* ---- diagnostics used by bench.py (not reference-facing) --------------------------- */
 unsigned long long dgmk_launch_count(void); /* kernels launched by this library so far */
 int dgmk_ffma_probe(const float* in, float* out, int blocks, int iters, void* stream);
+void dgmk_set_gemm_engine(int tensor_cores); /* 0: FFMA2 tiles only; 1 (default): tcgen05 3xTF32 where shapes allow */
+/* Bt holds three [N,K] copies back to back: plain | tf32-hi | tf32-lo */
+int dgmk_gemm_tc_probe(const float* A, const float* Bt, float* C, int64_t M, int N, int K, int64_t ld,
+                       void* stream);
 int dgmk_gemm_probe(const float* A, const float* B, float* C, int64_t M, int N, int K, int64_t ld,
                     void* stream);
 

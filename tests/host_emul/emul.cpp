@@ -11,9 +11,17 @@
 
 namespace {
 struct HostBackend {
+  bool bad_bt = false;
+  int64_t hl_stride = 0;
   explicit HostBackend(void*) {}
   template <class F> void ew(const F& f, int64_t n) { for (int64_t i = 0; i < n; ++i) f(i); }
-  void gemm_nn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M, int N, int K, bool acc) {
+  void gemm_nn(const float* A, int64_t lda, const float* B, int64_t ldb, const float* Bt, int64_t ldbt, float* C, int64_t ldc, int64_t M,
+               int N, int K, bool acc) {
+    // both packed orientations must describe the same matrix (checks the packing tables)
+    for (int k = 0; k < K; ++k) for (int n = 0; n < N; ++n) {
+      float b = B[(int64_t)k * ldb + n]; const float* t = Bt + (int64_t)n * ldbt + k;
+      if (b != t[0] || t[hl_stride] + t[2 * hl_stride] != b || t[hl_stride] != dgmk::tf32_round(b)) bad_bt = true;
+    }
     for (int64_t m = 0; m < M; ++m)
       for (int n = 0; n < N; ++n) {
         float s = 0.f;
@@ -57,7 +65,7 @@ struct HostBackend {
   void zero(void* p, size_t bytes) { memset(p, 0, bytes); }
   void copy(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
   bool is_device_ptr(const void*) { return true; }
-  const char* error() { return nullptr; }
+  const char* error() { return bad_bt ? "Bt != B^T" : nullptr; }
 };
 }  // namespace
 

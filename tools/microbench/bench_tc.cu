@@ -1,0 +1,82 @@
+// tcgen05 3xTF32 GEMM tile: correctness vs FP64 naive + throughput at the heat/DGM shapes.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cmath>
+#include "../../differential_equations_dnn_b200/csrc/dgmk_gemm_tc.cuh"
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+__global__ void naive_nt(const float* A, int64_t lda, const float* Bt, int64_t ldb, float* C, int64_t ldc, int64_t M, int N, int K, bool accum) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  int64_t m = idx / N; int n = idx % N;
+  double s = accum ? C[m * ldc + n] : 0.0;
+  for (int k = 0; k < K; ++k) s += (double)A[m * lda + k] * Bt[(int64_t)n * ldb + k];
+  C[m * ldc + n] = (float)s;
+}
+static double relerr(const std::vector<float>& a, const std::vector<float>& b) {
+  double num = 0, den = 0;
+  for (size_t i = 0; i < a.size(); ++i) { double d = (double)a[i] - b[i]; num += d * d; den += (double)b[i] * b[i]; }
+  return sqrt(num / (den + 1e-300));
+}
+template <typename F> float time_ms(F f, int reps) {
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; ++i) f();
+  CK(cudaDeviceSynchronize()); CK(cudaEventRecord(e0));
+  for (int i = 0; i < reps; ++i) f();
+  CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+  float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); return ms / reps;
+}
+int main() {
+  using namespace dgmk::tc;
+  CK(cudaFuncSetAttribute(gemm_nn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CK(cudaFuncSetAttribute(gemm_nn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  struct Case { int64_t M; int N, K; bool accum; };
+  Case cases[] = {{128, 128, 32, false}, {128, 128, 128, false}, {1000, 384, 128, false}, {777, 128, 384, true}};
+  for (auto c : cases) {
+    int64_t lda = c.K + 32, ldb = c.K, ldc = c.N + 64;
+    std::vector<float> hA(c.M * lda), hB((size_t)c.N * ldb * 3), hC(c.M * ldc);
+    srand(1);
+    for (auto& v : hA) v = (rand() / (float)RAND_MAX - 0.5f);
+    { size_t nb = (size_t)c.N * ldb; for (size_t i = 0; i < nb; ++i) { float v = (rand() / (float)RAND_MAX - 0.5f); union { float f; uint32_t u; } h; h.f = v; h.u = (h.u + 0x1000u) & 0xFFFFE000u; hB[i] = v; hB[nb + i] = h.f; hB[2 * nb + i] = v - h.f; } }
+    for (auto& v : hC) v = (rand() / (float)RAND_MAX - 0.5f);
+    float *A, *B, *C, *Cr;
+    CK(cudaMalloc(&A, hA.size() * 4)); CK(cudaMalloc(&B, hB.size() * 4));
+    CK(cudaMalloc(&C, hC.size() * 4)); CK(cudaMalloc(&Cr, hC.size() * 4));
+    CK(cudaMemcpy(A, hA.data(), hA.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(B, hB.data(), hB.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(C, hC.data(), hC.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(Cr, hC.data(), hC.size() * 4, cudaMemcpyHostToDevice));
+    naive_nt<<<(unsigned)((c.M * c.N + 255) / 256), 256>>>(A, lda, B, ldb, Cr, ldc, c.M, c.N, c.K, c.accum);
+    dim3 grid(c.N / BN, (unsigned)((c.M + BM - 1) / BM));
+    if (c.accum) gemm_nn_tc_kernel<true><<<grid, NT, SMEM_BYTES>>>(A, lda, B, ldb, (int64_t)c.N * ldb, C, ldc, c.M, c.K);
+    else gemm_nn_tc_kernel<false><<<grid, NT, SMEM_BYTES>>>(A, lda, B, ldb, (int64_t)c.N * ldb, C, ldc, c.M, c.K);
+    CK(cudaDeviceSynchronize());
+    std::vector<float> r1(hC.size()), r2(hC.size());
+    CK(cudaMemcpy(r1.data(), C, hC.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(r2.data(), Cr, hC.size() * 4, cudaMemcpyDeviceToHost));
+    printf("gemm_nn_tc M=%ld N=%d K=%d accum=%d relerr %.3e   C[0..3]= %g %g %g %g  ref %g %g %g %g\n", (long)c.M, c.N, c.K, c.accum,
+           relerr(r1, r2), r1[0], r1[1], r1[2], r1[3], r2[0], r2[1], r2[2], r2[3]);
+    cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(Cr);
+  }
+  {
+    int64_t M = 4LL << 17;
+    float *A, *B, *C;
+    CK(cudaMalloc(&A, M * 512 * 4)); CK(cudaMalloc(&B, 3 * 512 * 512 * 4)); CK(cudaMalloc(&C, M * 512 * 4));
+    CK(cudaMemset(A, 0, M * 512 * 4)); CK(cudaMemset(B, 0, 3 * 512 * 512 * 4));
+    struct T { const char* name; int N, K; bool acc; } ts[] = {
+        {"fwd ZGR  [M,128]x[128,384]", 384, 128, false}, {"fwd H    [M,128]x[128,128]", 128, 128, false},
+        {"dgrad ZGR[M,384]x[384,128]", 128, 384, true}};
+    for (auto t : ts) {
+      dim3 grid(t.N / BN, (unsigned)(M / BM));
+      float ms = time_ms([&] {
+        if (t.acc) gemm_nn_tc_kernel<true><<<grid, NT, SMEM_BYTES>>>(A, 512, B, t.K, (int64_t)512 * 512, C, 512, M, t.K);
+        else gemm_nn_tc_kernel<false><<<grid, NT, SMEM_BYTES>>>(A, 512, B, t.K, (int64_t)512 * 512, C, 512, M, t.K);
+      }, 10);
+      printf("%s: %.3f ms  %.2f TFLOP/s (fp32-equivalent)\n", t.name, ms, 2.0 * M * t.N * t.K / ms * 1e-9);
+    }
+    CK(cudaGetLastError());
+  }
+  printf("done\n");
+  return 0;
+}
