@@ -192,11 +192,18 @@ struct CudaBackend {
     int64_t splits = want < by_rows ? want : by_rows;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
-    int64_t rps = ((M + splits - 1) / splits + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
+    int64_t rps = ((M + splits - 1) / splits + 31) / 32 * 32;
     splits = (M + rps - 1) / rps;
     float* PE = E ? part + splits * tile : nullptr;
     dim3 grid(Kd / BN, (N + GEMM_BM - 1) / GEMM_BM, (unsigned)splits);
-    if (BN == 128) gemm_tn_kernel<128><<<grid, GEMM_NT, 0, st>>>(A, lda, S, lds, part, N, Kd, M, rps, E, PE);
+    if (use_tc && E && N % tc::BM == 0 && Kd % tc::BN == 0) {
+      static bool attr_done = false;
+      if (!attr_done) {
+        note(cudaFuncSetAttribute(tc::gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TN_SMEM_BYTES));
+        attr_done = true;
+      }
+      tc::gemm_tn_tc_kernel<<<grid, tc::NT, tc::TN_SMEM_BYTES, st>>>(A, lda, S, lds, E, part, PE, N, Kd, M, rps);
+    } else if (BN == 128) gemm_tn_kernel<128><<<grid, GEMM_NT, 0, st>>>(A, lda, S, lds, part, N, Kd, M, rps, E, PE);
     else if (BN == 64) gemm_tn_kernel<64><<<grid, GEMM_NT, 0, st>>>(A, lda, S, lds, part, N, Kd, M, rps, E, PE);
     else gemm_tn_kernel<32><<<grid, GEMM_NT, 0, st>>>(A, lda, S, lds, part, N, Kd, M, rps, E, PE);
     post();

@@ -75,7 +75,58 @@ int main() {
       }, 10);
       printf("%s: %.3f ms  %.2f TFLOP/s (fp32-equivalent)\n", t.name, ms, 2.0 * M * t.N * t.K / ms * 1e-9);
     }
+    {
+      CK(cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES));
+      int64_t rps = 4096; int splits = (int)(M / rps);
+      float *P, *PE, *E;
+      CK(cudaMalloc(&P, (size_t)splits * 384 * 128 * 4)); CK(cudaMalloc(&PE, (size_t)splits * 4 * 384 * 4)); CK(cudaMalloc(&E, M * 16));
+      CK(cudaMemset(E, 0, M * 16));
+      dim3 g2(1, 3, splits);
+      float ms = time_ms([&] { gemm_tn_tc_kernel<<<g2, NT, TN_SMEM_BYTES>>>(C, 512, A, 512, E, P, PE, 384, 128, M, rps); }, 10);
+      printf("wgrad ZGR [M,384]^T x [M,128] (tc): %.3f ms  %.2f TFLOP/s (fp32-equivalent)\n", ms, 2.0 * M * 384 * 128 / ms * 1e-9);
+    }
     CK(cudaGetLastError());
+  }
+  // ---- tn (weight gradient) tile ----
+  {
+    CK(cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES));
+    int64_t M = 1000; int N = 256, Kd = 128; int64_t lda = 512, lds = 128;
+    std::vector<float> hA(M * lda), hS(M * lds), hE(M * 4);
+    srand(3);
+    for (auto& v : hA) v = (rand() / (float)RAND_MAX - 0.5f);
+    for (auto& v : hS) v = (rand() / (float)RAND_MAX - 0.5f);
+    for (auto& v : hE) v = (rand() / (float)RAND_MAX - 0.5f);
+    float *A, *S, *E, *P, *PE;
+    int64_t rps = 256; int splits = (int)((M + rps - 1) / rps);
+    CK(cudaMalloc(&A, hA.size() * 4)); CK(cudaMalloc(&S, hS.size() * 4)); CK(cudaMalloc(&E, hE.size() * 4));
+    CK(cudaMalloc(&P, (size_t)splits * N * Kd * 4)); CK(cudaMalloc(&PE, (size_t)splits * 4 * N * 4));
+    CK(cudaMemcpy(A, hA.data(), hA.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(S, hS.data(), hS.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(E, hE.data(), hE.size() * 4, cudaMemcpyHostToDevice));
+    dim3 grid(Kd / 128, N / 128, splits);
+    {
+    gemm_tn_tc_kernel<<<grid, NT, TN_SMEM_BYTES>>>(A, lda, S, lds, E, P, PE, N, Kd, M, rps);
+    CK(cudaDeviceSynchronize());
+    std::vector<float> hP((size_t)splits * N * Kd), hPE((size_t)splits * 4 * N);
+    CK(cudaMemcpy(hP.data(), P, hP.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hPE.data(), PE, hPE.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<float> g((size_t)N * Kd), gr((size_t)N * Kd), ge(4 * N), ger(4 * N);
+    for (int n = 0; n < N; ++n) for (int k = 0; k < Kd; ++k) {
+      double s = 0, r = 0;
+      for (int z = 0; z < splits; ++z) s += hP[((size_t)z * N + n) * Kd + k];
+      for (int64_t m = 0; m < M; ++m) r += (double)hA[m * lda + n] * hS[m * lds + k];
+      g[(size_t)n * Kd + k] = (float)s; gr[(size_t)n * Kd + k] = (float)r;
+    }
+    for (int e = 0; e < 4; ++e) for (int n = 0; n < N; ++n) {
+      double s = 0, r = 0;
+      for (int z = 0; z < splits; ++z) s += hPE[((size_t)z * 4 + e) * N + n];
+      for (int64_t m = 0; m < M; ++m) r += (double)hA[m * lda + n] * hE[m * 4 + e];
+      ge[e * N + n] = (float)s; ger[e * N + n] = (float)r;
+    }
+    printf("gemm_tn_tc M=%ld N=%d Kd=%d relerr W %.3e  E %.3e   g[0..3]= %g %g %g %g ref %g %g %g %g\n", (long)M, N, Kd, relerr(g, gr), relerr(ge, ger),
+           g[0], g[1], g[2], g[3], gr[0], gr[1], gr[2], gr[3]);
+    printf("   g[128*Kd..]= %g %g ref %g %g ; ge[0..1]= %g %g ref %g %g\n", g[128 * Kd], g[128 * Kd + 1], gr[128 * Kd], gr[128 * Kd + 1], ge[0], ge[1], ger[0], ger[1]);
+    }
   }
   printf("done\n");
   return 0;
