@@ -35,7 +35,8 @@ constexpr int NT = 128;
 constexpr int LBO = 2048 + 16;            // bytes between core matrices adjacent in K (padded: conflict-free)
 constexpr int SBO = 128;                  // bytes between 8-row groups
 constexpr int OPER_BYTES = (KC / 4) * LBO;  // one [128 x 32] operand tile
-constexpr int SMEM_BYTES = 4 * OPER_BYTES + 64;
+constexpr int CPITCH = BN + 4;                 // floats per row of the epilogue staging tile
+constexpr int SMEM_BYTES = (4 * OPER_BYTES > BM * CPITCH * 4 ? 4 * OPER_BYTES : BM * CPITCH * 4) + 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -95,10 +96,10 @@ __global__ void __launch_bounds__(NT) gemm_nn_tc_kernel(const float* __restrict_
   char* sAl = smem + OPER_BYTES;
   char* sBh = smem + 2 * OPER_BYTES;
   char* sBl = smem + 3 * OPER_BYTES;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 4 * OPER_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 4 * OPER_BYTES + 16);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SMEM_BYTES - 64);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_BYTES - 48);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t m0 = (int64_t)blockIdx.y * BM;
   const int n0 = blockIdx.x * BN;
   const uint32_t bar_a = smem_u32(bar);
@@ -207,15 +208,34 @@ __global__ void __launch_bounds__(NT) gemm_nn_tc_kernel(const float* __restrict_
   mbar_wait(bar_a, phase);
   drain();
 
-  // epilogue: thread t owns output row t
-  if (a_ok) {
-    float* crow = C + am * ldc + n0;
+  // epilogue: thread t owns output row t.  Rows go through shared memory (the operand
+  // tiles are dead now) so that each warp stores whole 512-byte rows instead of 32
+  // scattered 16-byte pieces per instruction.
+  {
+    float* stile = reinterpret_cast<float*>(smem);
 #pragma unroll
-    for (int q = 0; q < BN / 4; ++q) {
-      float4* p = reinterpret_cast<float4*>(crow + q * 4);
-      float4 o = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-      if (ACCUM) { float4 old = *p; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-      *p = o;
+    for (int q = 0; q < BN / 4; ++q)
+      *reinterpret_cast<float4*>(stile + tid * CPITCH + q * 4) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    __syncwarp();  // each warp only re-reads the 32 rows it wrote itself
+    for (int rb = 0; rb < 32; rb += 8) {   // batches of 8 rows: all loads in flight before the stores
+      float4 old[8];
+      if (ACCUM) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int row = warp * 32 + rb + r;
+          old[r] = (m0 + row < M) ? *reinterpret_cast<const float4*>(C + (m0 + row) * ldc + n0 + lane * 4)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int row = warp * 32 + rb + r;
+        if (m0 + row < M) {
+          float4 o = *reinterpret_cast<const float4*>(stile + row * CPITCH + lane * 4);
+          if (ACCUM) { o.x += old[r].x; o.y += old[r].y; o.z += old[r].z; o.w += old[r].w; }
+          *reinterpret_cast<float4*>(C + (m0 + row) * ldc + n0 + lane * 4) = o;
+        }
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
