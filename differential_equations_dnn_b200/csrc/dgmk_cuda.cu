@@ -66,8 +66,25 @@ __global__ void __launch_bounds__(128) wcolsum_kernel(const float* __restrict__ 
       __syncthreads();
     }
     if (n < N) {
-#pragma unroll 4
-      for (int q = 0; q < cnt; ++q) {
+      int q = 0;
+      for (; q + 8 <= cnt; q += 8) {   // 8 independent loads in flight per thread
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(Mat + (rb + q + u) * ldm + n);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (WEIGHTED) {
+            float4 w = wsm[q + u];
+            acc[0] = fmaf(w.x, v[u], acc[0]);
+            acc[1] = fmaf(w.y, v[u], acc[1]);
+            acc[2] = fmaf(w.z, v[u], acc[2]);
+            acc[NE - 1] = fmaf(w.w, v[u], acc[NE - 1]);
+          } else {
+            acc[0] += v[u];
+          }
+        }
+      }
+      for (; q < cnt; ++q) {
         float v = __ldg(Mat + (rb + q) * ldm + n);
         if (WEIGHTED) {
           float4 w = wsm[q];
@@ -221,7 +238,7 @@ struct CudaBackend {
     if (max_blk > 512) max_blk = 512;
     if (max_blk < 1) { if (!err) err = "internal: partial buffer too small"; return; }
     const int ctiles = (N + 127) / 128;
-    int64_t want = ((int64_t)sms * 8 + ctiles - 1) / ctiles;
+    int64_t want = ((int64_t)sms * 16 + ctiles - 1) / ctiles;
     int64_t by_rows = (M + 255) / 256;
     int64_t nblk = want < by_rows ? want : by_rows;
     if (nblk > max_blk) nblk = max_blk;

@@ -24,7 +24,8 @@ struct XSrc {
   int64_t block_stride;  // floats between consecutive blocks when nptr == 1
   int32_t nptr, d;
   DGMK_HD const float* at(int64_t r) const {
-    int64_t b = r / block_rows, w = r - b * block_rows;
+    int64_t b = (nptr == 1 && r < block_rows) ? 0 : ((block_rows >> 31) == 0 ? idiv(r, (int32_t)block_rows) : r / block_rows);
+    int64_t w = r - b * block_rows;
     // ternaries, not p[b]: a runtime index would spill the parameter array to local memory
     const float* base = (nptr > 1) ? (b == 0 ? p[0] : (b == 1 ? p[1] : p[2])) : p[0] + b * block_stride;
     return base + w * d;
@@ -95,7 +96,7 @@ template <class CS, int ACT>
 struct InputFwdFn {
   XSrc xs; const F4* inb; float* S0; int Hp;
   DGMK_HD void operator()(int64_t i) const {
-    int64_t p = i / Hp; int j = (int)(i - p * Hp);
+    int64_t p = idiv(i, Hp); int j = (int)(i - p * Hp);
     const float* x = xs.at(p);
     F4 w = inb[j];
     float a[CS::C], y[CS::C];
@@ -115,7 +116,7 @@ template <class CS, int ACT>
 struct InputRevFn {
   const F4* inb; const float* S0; const float* SB; float* AB; int Hp; int64_t ldab;
   DGMK_HD void operator()(int64_t i) const {
-    int64_t p = i / Hp; int j = (int)(i - p * Hp);
+    int64_t p = idiv(i, Hp); int j = (int)(i - p * Hp);
     F4 w = inb[j];
     float af[CS::C], yb[CS::C], ab[CS::C];
     af[0] = S0[(p * CS::C) * Hp + j];
@@ -136,7 +137,7 @@ template <class CS, int ACT>
 struct MlpActFn {
   float* G; const F4* ub; float* Yn; int Hp;  // G: GEMM output -> a-form in place
   DGMK_HD void operator()(int64_t i) const {
-    int64_t p = i / Hp; int j = (int)(i - p * Hp);
+    int64_t p = idiv(i, Hp); int j = (int)(i - p * Hp);
     float a[CS::C], y[CS::C];
     float* g = G + (p * CS::C) * Hp + j;
 #pragma unroll
@@ -153,7 +154,7 @@ template <class CS, int ACT>
 struct MlpRevFn {
   const float* G; const float* YB; float* AB; int Hp;
   DGMK_HD void operator()(int64_t i) const {
-    int64_t p = i / Hp; int j = (int)(i - p * Hp);
+    int64_t p = idiv(i, Hp); int j = (int)(i - p * Hp);
     float af[CS::C], yb[CS::C], ab[CS::C];
     int64_t base = (p * CS::C) * Hp + j;
 #pragma unroll
@@ -178,7 +179,7 @@ template <class CS, int ACT>
 struct DgmFwd1Fn {
   XSrc xs; float* A4; const F4* ub; const float* S; float* SR; int Hp;
   DGMK_HD void operator()(int64_t i) const {
-    int64_t p = i / Hp; int j = (int)(i - p * Hp);
+    int64_t p = idiv(i, Hp); int j = (int)(i - p * Hp);
     const float* x = xs.at(p);
     const int64_t ld = 4 * (int64_t)Hp;
     float a[CS::C], y[CS::C];
@@ -208,7 +209,7 @@ template <class CS, int ACT>
 struct DgmFwd2Fn {
   XSrc xs; float* A4; const F4* ub; const float* S; float* Sn; int Hp;
   DGMK_HD void operator()(int64_t i) const {
-    int64_t p = i / Hp; int j = (int)(i - p * Hp);
+    int64_t p = idiv(i, Hp); int j = (int)(i - p * Hp);
     const float* x = xs.at(p);
     const int64_t ld = 4 * (int64_t)Hp;
     float a[CS::C], h[CS::C], z[CS::C], g[CS::C], s[CS::C], t1[CS::C], t2[CS::C];
@@ -241,7 +242,7 @@ template <class CS, int ACT>
 struct DgmRev1Fn {
   const float* A4; const float* S; const float* SBn; float* AB4; float* SBp; int Hp;
   DGMK_HD void operator()(int64_t i) const {
-    int64_t p = i / Hp; int j = (int)(i - p * Hp);
+    int64_t p = idiv(i, Hp); int j = (int)(i - p * Hp);
     const int64_t ld = 4 * (int64_t)Hp;
     const float* row = A4 + (p * CS::C) * ld + j;
     float* orow = AB4 + (p * CS::C) * ld + j;
@@ -283,7 +284,7 @@ template <class CS, int ACT>
 struct DgmRev2Fn {
   const float* A4; const float* S; const float* SRB; float* AB4; float* SBp; int Hp;
   DGMK_HD void operator()(int64_t i) const {
-    int64_t p = i / Hp; int j = (int)(i - p * Hp);
+    int64_t p = idiv(i, Hp); int j = (int)(i - p * Hp);
     const int64_t ld = 4 * (int64_t)Hp;
     const float* row = A4 + (p * CS::C) * ld + 2 * Hp + j;
     float* orow = AB4 + (p * CS::C) * ld + 2 * Hp + j;
@@ -309,7 +310,7 @@ struct DgmRev2Fn {
 struct OutRevFn {
   const float* UB; const float* outw; float* SB; int Hp; int o;
   DGMK_HD void operator()(int64_t i) const {
-    int64_t r = i / Hp; int j = (int)(i - r * Hp);
+    int64_t r = idiv(i, Hp); int j = (int)(i - r * Hp);
     float v = 0.f;
     for (int m = 0; m < o; ++m) v += UB[r * 4 + m] * outw[m * Hp + j];
     SB[i] = v;
@@ -339,7 +340,7 @@ struct ValueTargetFn {
   const float* U; float* UB; float* Lp; XSrc xs; const float* tgt[3]; int32_t mode[3];
   int32_t o; float inv;
   DGMK_HD void operator()(int64_t p) const {
-    int64_t b = p / xs.block_rows, w = p - b * xs.block_rows;
+    int64_t b = (xs.block_rows >> 31) == 0 ? idiv(p, (int32_t)xs.block_rows) : p / xs.block_rows, w = p - b * xs.block_rows;
     float l = 0.f;
     for (int m = 0; m < 4; ++m) {
       float ubv = 0.f;
