@@ -104,12 +104,13 @@ __global__ void __launch_bounds__(NT) gemm_nn_tc_kernel(const float* __restrict_
   const int n0 = blockIdx.x * BN;
   const uint32_t bar_a = smem_u32(bar);
 
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(BN) : "memory");
+  if (warp == 0) {  // two accumulator buffers: chunk c+1 is multiplied while chunk c is drained
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(2 * BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   if (tid == 0) {
     mbar_init(bar_a, 1);
+    mbar_init(bar_a + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -149,12 +150,12 @@ __global__ void __launch_bounds__(NT) gemm_nn_tc_kernel(const float* __restrict_
 #pragma unroll
   for (int j = 0; j < BN; ++j) acc[j] = 0.f;
   // chunk result TMEM -> registers, added in RN (cuts the tensor core's truncating chain)
-  auto drain = [&]() {
+  auto drain = [&](int buf) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll
     for (int cb = 0; cb < BN / 32; ++cb) {
       uint32_t v[32];
-      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32);
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN + cb * 32);
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
           "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -172,13 +173,12 @@ __global__ void __launch_bounds__(NT) gemm_nn_tc_kernel(const float* __restrict_
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   };
   const int nchunks = K / KC;
-  uint32_t phase = 0;
+  uint32_t phase0 = 0, phase1 = 0;   // parity of the next completion of each buffer's barrier
   load_chunk(0);
   for (int c = 0; c < nchunks; ++c) {
-    if (c > 0) {  // previous chunk's MMAs are done: shared memory is free and its result is in TMEM
-      mbar_wait(bar_a, phase);
-      phase ^= 1;
-      drain();
+    const int buf = c & 1;
+    if (c > 0) {  // MMAs of chunk c-1 done: shared memory is free, its result sits in TMEM buffer buf^1
+      if (buf) { mbar_wait(bar_a, phase0); phase0 ^= 1; } else { mbar_wait(bar_a + 8, phase1); phase1 ^= 1; }
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) split_store(sAh, sAl, st_off + q * 2 * SBO, ra[q]);
@@ -191,22 +191,27 @@ __global__ void __launch_bounds__(NT) gemm_nn_tc_kernel(const float* __restrict_
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const uint64_t dAh = make_desc(smem_u32(sAh)), dAl = make_desc(smem_u32(sAl));
       const uint64_t dBh = make_desc(smem_u32(sBh)), dBl = make_desc(smem_u32(sBl));
+      const uint32_t d = tmem + (uint32_t)(buf * BN);
 #pragma unroll
       for (int ks = 0; ks < KC / 8; ++ks) {  // small terms first
         const uint64_t adv = (uint64_t)((ks * 2 * LBO) >> 4);  // two core matrices along K per k-step
-        mma_tf32(tmem, dAl + adv, dBh + adv, ks > 0 ? 1u : 0u);
-        mma_tf32(tmem, dAh + adv, dBl + adv, 1u);
+        mma_tf32(d, dAl + adv, dBh + adv, ks > 0 ? 1u : 0u);
+        mma_tf32(d, dAh + adv, dBl + adv, 1u);
       }
 #pragma unroll
       for (int ks = 0; ks < KC / 8; ++ks) {
         const uint64_t adv = (uint64_t)((ks * 2 * LBO) >> 4);
-        mma_tf32(tmem, dAh + adv, dBh + adv, 1u);
+        mma_tf32(d, dAh + adv, dBh + adv, 1u);
       }
-      mma_commit(bar_a);
+      mma_commit(bar_a + 8 * buf);
     }
+    if (c > 0) drain(buf ^ 1);   // overlaps the MMAs just issued
   }
-  mbar_wait(bar_a, phase);
-  drain();
+  {
+    const int buf = (nchunks - 1) & 1;
+    if (buf) mbar_wait(bar_a + 8, phase1); else mbar_wait(bar_a, phase0);
+    drain(buf);
+  }
 
   // epilogue: thread t owns output row t.  Rows go through shared memory (the operand
   // tiles are dead now) so that each warp stores whole 512-byte rows instead of 32
@@ -241,7 +246,7 @@ __global__ void __launch_bounds__(NT) gemm_nn_tc_kernel(const float* __restrict_
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(2 * BN) : "memory");
   }
 }
 
@@ -249,8 +254,8 @@ __global__ void __launch_bounds__(NT) gemm_nn_tc_kernel(const float* __restrict_
 // =====================================================================================
 // Weight gradient on tcgen05:   P[z][N,Kd] = sum_{m in split z} A[m,0:N]^T S[m,0:Kd]
 //                               PE[z][4,N] = sum_m A[m,n] E[m,e]      (input-map / bias grads)
-// UMMA M = 128 columns of A (output rows), UMMA N = 128 columns of S + 32 extra columns that
-// carry E (so grad[W | U | b] comes out of ONE accumulator), UMMA K = rows.  Both operands are
+// UMMA M = 128 columns of A (output rows), UMMA N = 128 columns of S, UMMA K = rows; A^T E is
+// accumulated next to it on the CUDA cores from the values being staged.  Both operands are
 // MN-major straight out of the row-major activations (idesc a_major = b_major = 1).  For
 // 32-bit MN-major operands the only layout the tensor core accepts is SWIZZLE_128B_BASE32B
 // (no-swizzle MN-major tf32 silently yields zeros -- measured): atoms of 4 rows x 128 bytes
@@ -260,24 +265,19 @@ __global__ void __launch_bounds__(NT) gemm_nn_tc_kernel(const float* __restrict_
 // with no transposition.  Same 3xTF32 split and per-chunk (32 rows) RN drain as above.
 // grid = (Kd / 128, N / 128, splits); N, Kd multiples of 128; E row stride 4 floats.
 constexpr int TN_LBO = 512;                       // bytes between 32-column groups
-constexpr int TN_GROUPS_A = 4;                    // 128 columns
-constexpr int TN_GROUPS_B = 5;                    // 128 columns of S + 32 columns for E
-constexpr int TN_SBO_A = TN_GROUPS_A * TN_LBO;    // bytes between 4-row groups
-constexpr int TN_SBO_B = TN_GROUPS_B * TN_LBO;
-constexpr int TN_A_BYTES = (KC / 4) * TN_SBO_A;   // 16 KB
-constexpr int TN_B_BYTES = (KC / 4) * TN_SBO_B;   // 20 KB
-constexpr int TN_SMEM_BYTES = 2 * TN_A_BYTES + 2 * TN_B_BYTES + 64 + 1024;
-constexpr int TN_NCOLS = BN + 32;                 // accumulator columns
+constexpr int TN_SBO = 4 * TN_LBO;                // bytes between 4-row groups (128 columns per operand)
+constexpr int TN_OPER_BYTES = (KC / 4) * TN_SBO;  // 16 KB
+constexpr int TN_SMEM_BYTES = 4 * TN_OPER_BYTES + 32 + 2 * 32 * 16 + 1024;
 constexpr uint32_t TN_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                              ((uint32_t)(TN_NCOLS >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, int sbo) {
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((TN_LBO >> 4) & 0x3FFF) << 16;  // leading: MN direction (32-column groups)
-  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;     // stride: K direction (4-row groups)
+  d |= (uint64_t)((TN_SBO >> 4) & 0x3FFF) << 32;  // stride: K direction (4-row groups)
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)1 << 61;                                        // SWIZZLE_128B_BASE32B
+  d |= (uint64_t)1 << 61;                         // SWIZZLE_128B_BASE32B
   return d;
 }
 __device__ __forceinline__ void mma_tf32_tn(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
@@ -288,8 +288,8 @@ __device__ __forceinline__ void mma_tf32_tn(uint32_t d_tmem, uint64_t adesc, uin
       : "memory");
 }
 // byte offset of the 16-byte piece (row m of the chunk, columns col..col+3) inside an operand tile
-__device__ __forceinline__ int tn_off(int m, int col, int sbo) {
-  return (m >> 2) * sbo + (col >> 5) * TN_LBO + (m & 3) * 128 + ((((col & 31) >> 3) ^ (m & 3)) << 5) + ((col & 7) << 2);
+__device__ __forceinline__ int tn_off(int m, int col) {
+  return (m >> 2) * TN_SBO + (col >> 5) * TN_LBO + (m & 3) * 128 + ((((col & 31) >> 3) ^ (m & 3)) << 5) + ((col & 7) << 2);
 }
 
 __global__ void __launch_bounds__(NT) gemm_tn_tc_kernel(const float* __restrict__ A, int64_t lda,
@@ -300,11 +300,11 @@ __global__ void __launch_bounds__(NT) gemm_tn_tc_kernel(const float* __restrict_
   extern __shared__ char smem_raw[];
   char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   char* sAh = smem;
-  char* sAl = smem + TN_A_BYTES;
-  char* sBh = smem + 2 * TN_A_BYTES;
-  char* sBl = smem + 2 * TN_A_BYTES + TN_B_BYTES;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * TN_A_BYTES + 2 * TN_B_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 2 * TN_A_BYTES + 2 * TN_B_BYTES + 16);
+  char* sAl = smem + TN_OPER_BYTES;
+  char* sBh = smem + 2 * TN_OPER_BYTES;
+  char* sBl = smem + 3 * TN_OPER_BYTES;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 4 * TN_OPER_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 4 * TN_OPER_BYTES + 16);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int i0 = blockIdx.y * BM;   // output rows  = columns of A
@@ -312,20 +312,16 @@ __global__ void __launch_bounds__(NT) gemm_tn_tc_kernel(const float* __restrict_
   const int64_t mb = (int64_t)blockIdx.z * rows_per_split;
   const int64_t me = (mb + rows_per_split < M) ? mb + rows_per_split : M;
   const uint32_t bar_a = smem_u32(bar);
+  const bool do_e = (PE != nullptr) && (blockIdx.x == 0);
 
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(256) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(2 * BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   if (tid == 0) {
     mbar_init(bar_a, 1);
+    mbar_init(bar_a + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-  // the E column group (columns 128..159): only columns 128..131 are ever written, the rest stay zero
-  for (int i = tid; i < KC * 8; i += NT) {
-    const int off = tn_off(i >> 3, 128 + (i & 7) * 4, TN_SBO_B);
-    *reinterpret_cast<float4*>(sBh + off) = make_float4(0.f, 0.f, 0.f, 0.f);
-    *reinterpret_cast<float4*>(sBl + off) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
@@ -336,6 +332,7 @@ __global__ void __launch_bounds__(NT) gemm_tn_tc_kernel(const float* __restrict_
   const float* abase = A + i0 + lane * 4;
   const float* sbase = S + j0 + lane * 4;
   float4 ra[8], rs[8], re;
+  float4* sE = reinterpret_cast<float4*>(smem + 4 * TN_OPER_BYTES + 32);   // [2][32] rows of E, double-buffered
   auto load_chunk = [&](int64_t m0) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -344,20 +341,27 @@ __global__ void __launch_bounds__(NT) gemm_tn_tc_kernel(const float* __restrict_
       ra[q] = ok ? __ldg(reinterpret_cast<const float4*>(abase + m * lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
       rs[q] = ok ? __ldg(reinterpret_cast<const float4*>(sbase + m * lds)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (tid < KC) {
+    if (do_e && tid < KC) {
       const int64_t m = m0 + tid;
       re = (m < me) ? __ldg(reinterpret_cast<const float4*>(E) + m) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
-  float acc[BN + 4];
+  float acc[BN];
 #pragma unroll
-  for (int j = 0; j < BN + 4; ++j) acc[j] = 0.f;
-  auto drain = [&]() {
+  for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+  // grad[U | b] = A^T E on the CUDA cores, from the A values this thread stages anyway:
+  // eacc[x][e] for columns lane*4 + x; the four warps hold different rows and are summed at the end
+  float eacc[4][4];
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) eacc[x][e] = 0.f;
+  auto drain = [&](int buf) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll
     for (int cb = 0; cb < 4; ++cb) {
       uint32_t v[32];
-      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32);
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN + cb * 32);
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
           "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -372,61 +376,68 @@ __global__ void __launch_bounds__(NT) gemm_tn_tc_kernel(const float* __restrict_
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[cb * 32 + j] += __uint_as_float(v[j]);
     }
-    {
-      uint32_t v[4];
-      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + 128u;
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
-                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
-                   : "r"(taddr)
-                   : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[128 + j] += __uint_as_float(v[j]);
-    }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   };
 
   const int64_t nchunks = (me - mb + KC - 1) / KC;
-  uint32_t phase = 0;
+  uint32_t phase0 = 0, phase1 = 0;
   if (nchunks > 0) load_chunk(mb);
   for (int64_t c = 0; c < nchunks; ++c) {
+    const int buf = (int)(c & 1);
     if (c > 0) {
-      mbar_wait(bar_a, phase);
-      phase ^= 1;
-      drain();
+      if (buf) { mbar_wait(bar_a, phase0); phase0 ^= 1; } else { mbar_wait(bar_a + 8, phase1); phase1 ^= 1; }
+    }
+    if (do_e) {   // this chunk's E rows -> shared memory (consumed after the barrier below)
+      if (tid < KC) sE[buf * KC + tid] = re;
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int row = q * 4 + warp;
-      split_store(sAh, sAl, tn_off(row, lane * 4, TN_SBO_A), ra[q]);
-      split_store(sBh, sBl, tn_off(row, lane * 4, TN_SBO_B), rs[q]);
+      split_store(sAh, sAl, tn_off(row, lane * 4), ra[q]);
+      split_store(sBh, sBl, tn_off(row, lane * 4), rs[q]);
     }
-    if (tid < KC) split_store(sBh, sBl, tn_off(tid, 128, TN_SBO_B), re);
-    if (c + 1 < nchunks) load_chunk(mb + (c + 1) * KC);
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const uint64_t dAh = make_desc_mn(smem_u32(sAh), TN_SBO_A), dAl = make_desc_mn(smem_u32(sAl), TN_SBO_A);
-      const uint64_t dBh = make_desc_mn(smem_u32(sBh), TN_SBO_B), dBl = make_desc_mn(smem_u32(sBl), TN_SBO_B);
+      const uint64_t dAh = make_desc_mn(smem_u32(sAh)), dAl = make_desc_mn(smem_u32(sAl));
+      const uint64_t dBh = make_desc_mn(smem_u32(sBh)), dBl = make_desc_mn(smem_u32(sBl));
+      const uint32_t d = tmem + (uint32_t)(buf * BN);
 #pragma unroll
       for (int ks = 0; ks < KC / 8; ++ks) {  // small terms first; a k-step of 8 rows = two 4-row groups
-        const uint64_t aa = (uint64_t)((ks * 2 * TN_SBO_A) >> 4), ab = (uint64_t)((ks * 2 * TN_SBO_B) >> 4);
-        mma_tf32_tn(tmem, dAl + aa, dBh + ab, ks > 0 ? 1u : 0u);
-        mma_tf32_tn(tmem, dAh + aa, dBl + ab, 1u);
+        const uint64_t adv = (uint64_t)((ks * 2 * TN_SBO) >> 4);
+        mma_tf32_tn(d, dAl + adv, dBh + adv, ks > 0 ? 1u : 0u);
+        mma_tf32_tn(d, dAh + adv, dBl + adv, 1u);
       }
 #pragma unroll
       for (int ks = 0; ks < KC / 8; ++ks) {
-        const uint64_t aa = (uint64_t)((ks * 2 * TN_SBO_A) >> 4), ab = (uint64_t)((ks * 2 * TN_SBO_B) >> 4);
-        mma_tf32_tn(tmem, dAh + aa, dBh + ab, 1u);
+        const uint64_t adv = (uint64_t)((ks * 2 * TN_SBO) >> 4);
+        mma_tf32_tn(d, dAh + adv, dBh + adv, 1u);
       }
-      mma_commit(bar_a);
+      mma_commit(bar_a + 8 * buf);
     }
+    if (do_e) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 ev = sE[buf * KC + q * 4 + warp];
+        const float av[4] = {ra[q].x, ra[q].y, ra[q].z, ra[q].w};
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          eacc[x][0] = fmaf(av[x], ev.x, eacc[x][0]);
+          eacc[x][1] = fmaf(av[x], ev.y, eacc[x][1]);
+          eacc[x][2] = fmaf(av[x], ev.z, eacc[x][2]);
+          eacc[x][3] = fmaf(av[x], ev.w, eacc[x][3]);
+        }
+      }
+    }
+    if (c + 1 < nchunks) load_chunk(mb + (c + 1) * KC);   // a whole iteration ahead of its use
+    if (c > 0) drain(buf ^ 1);
   }
   if (nchunks > 0) {
-    mbar_wait(bar_a, phase);
-    drain();
+    const int buf = (int)((nchunks - 1) & 1);
+    if (buf) mbar_wait(bar_a + 8, phase1); else mbar_wait(bar_a, phase0);
+    drain(buf);
   }
   // thread t owns output row i0 + t
   {
@@ -434,16 +445,23 @@ __global__ void __launch_bounds__(NT) gemm_tn_tc_kernel(const float* __restrict_
 #pragma unroll
     for (int q = 0; q < BN / 4; ++q)
       *reinterpret_cast<float4*>(prow + q * 4) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-    if (blockIdx.x == 0 && PE != nullptr) {
-      float* pe = PE + (int64_t)blockIdx.z * 4 * N + i0 + tid;
+  }
+  if (do_e) {  // sum the four warps' partial A^T E through shared memory (operand tiles are dead)
+    float* se = reinterpret_cast<float*>(smem);   // [warp][e][128]
 #pragma unroll
-      for (int e = 0; e < 4; ++e) pe[(int64_t)e * N] = acc[128 + e];
-    }
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) se[(warp * 4 + e) * BN + lane * 4 + x] = eacc[x][e];
+    __syncthreads();
+    float* pe = PE + (int64_t)blockIdx.z * 4 * N + i0 + tid;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      pe[(int64_t)e * N] = (se[(0 * 4 + e) * BN + tid] + se[(1 * 4 + e) * BN + tid]) + (se[(2 * 4 + e) * BN + tid] + se[(3 * 4 + e) * BN + tid]);
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(256) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(2 * BN) : "memory");
   }
 }
 
