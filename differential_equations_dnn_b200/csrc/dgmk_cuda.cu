@@ -6,6 +6,7 @@
 #include "dgmk_capi_impl.h"
 #include "dgmk_gemm.cuh"
 #include "dgmk_gemm_tc.cuh"
+#include "dgmk_gemm_tc_tn.cuh"
 
 namespace dgmk {
 
@@ -216,10 +217,10 @@ struct CudaBackend {
     if (use_tc && E && N % tc::BM == 0 && Kd % tc::BN == 0) {
       static bool attr_done = false;
       if (!attr_done) {
-        note(cudaFuncSetAttribute(tc::gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TN_SMEM_BYTES));
+        note(cudaFuncSetAttribute(tctn::gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tctn::TN_SMEM_BYTES));
         attr_done = true;
       }
-      tc::gemm_tn_tc_kernel<<<grid, tc::NT, tc::TN_SMEM_BYTES, st>>>(A, lda, S, lds, E, part, PE, N, Kd, M, rps);
+      tctn::gemm_tn_tc_kernel<<<grid, tctn::NT, tctn::TN_SMEM_BYTES, st>>>(A, lda, S, lds, E, part, PE, N, Kd, M, rps);
     } else if (BN == 128) gemm_tn_kernel<128><<<grid, GEMM_NT, 0, st>>>(A, lda, S, lds, part, N, Kd, M, rps, E, PE);
     else if (BN == 64) gemm_tn_kernel<64><<<grid, GEMM_NT, 0, st>>>(A, lda, S, lds, part, N, Kd, M, rps, E, PE);
     else gemm_tn_kernel<32><<<grid, GEMM_NT, 0, st>>>(A, lda, S, lds, part, N, Kd, M, rps, E, PE);

@@ -4,6 +4,7 @@
 #include <vector>
 #include <cmath>
 #include "../../differential_equations_dnn_b200/csrc/dgmk_gemm_tc.cuh"
+#include "../../differential_equations_dnn_b200/csrc/dgmk_gemm_tc_tn.cuh"
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
 __global__ void naive_nt(const float* A, int64_t lda, const float* Bt, int64_t ldb, float* C, int64_t ldc, int64_t M, int N, int K, bool accum) {
@@ -76,20 +77,20 @@ int main() {
       printf("%s: %.3f ms  %.2f TFLOP/s (fp32-equivalent)\n", t.name, ms, 2.0 * M * t.N * t.K / ms * 1e-9);
     }
     {
-      CK(cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES));
+      CK(cudaFuncSetAttribute(dgmk::tctn::gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dgmk::tctn::TN_SMEM_BYTES));
       int64_t rps = 4096; int splits = (int)(M / rps);
       float *P, *PE, *E;
       CK(cudaMalloc(&P, (size_t)splits * 384 * 128 * 4)); CK(cudaMalloc(&PE, (size_t)splits * 4 * 384 * 4)); CK(cudaMalloc(&E, M * 16));
       CK(cudaMemset(E, 0, M * 16));
       dim3 g2(1, 3, splits);
-      float ms = time_ms([&] { gemm_tn_tc_kernel<<<g2, NT, TN_SMEM_BYTES>>>(C, 512, A, 512, E, P, PE, 384, 128, M, rps); }, 10);
+      float ms = time_ms([&] { dgmk::tctn::gemm_tn_tc_kernel<<<g2, dgmk::tctn::NT, dgmk::tctn::TN_SMEM_BYTES>>>(C, 512, A, 512, E, P, PE, 384, 128, M, rps); }, 10);
       printf("wgrad ZGR [M,384]^T x [M,128] (tc): %.3f ms  %.2f TFLOP/s (fp32-equivalent)\n", ms, 2.0 * M * 384 * 128 / ms * 1e-9);
     }
     CK(cudaGetLastError());
   }
   // ---- tn (weight gradient) tile ----
   {
-    CK(cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(dgmk::tctn::gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dgmk::tctn::TN_SMEM_BYTES));
     int64_t M = 1000; int N = 256, Kd = 128; int64_t lda = 512, lds = 128;
     std::vector<float> hA(M * lda), hS(M * lds), hE(M * 4);
     srand(3);
@@ -105,7 +106,7 @@ int main() {
     CK(cudaMemcpy(E, hE.data(), hE.size() * 4, cudaMemcpyHostToDevice));
     dim3 grid(Kd / 128, N / 128, splits);
     {
-    gemm_tn_tc_kernel<<<grid, NT, TN_SMEM_BYTES>>>(A, lda, S, lds, E, P, PE, N, Kd, M, rps);
+    dgmk::tctn::gemm_tn_tc_kernel<<<grid, dgmk::tctn::NT, dgmk::tctn::TN_SMEM_BYTES>>>(A, lda, S, lds, E, P, PE, N, Kd, M, rps);
     CK(cudaDeviceSynchronize());
     std::vector<float> hP((size_t)splits * N * Kd), hPE((size_t)splits * 4 * N);
     CK(cudaMemcpy(hP.data(), P, hP.size() * 4, cudaMemcpyDeviceToHost));
