@@ -67,7 +67,7 @@ inline int64_t loss_points(int cls, int64_t ch, int k) {
 inline size_t total_bytes(const Ctx& c, int cls, int64_t ch, int k) {
   return ctx_bytes(c.n, c.pl, loss_points(cls, ch, k)) + chunk_region_bytes(c.n, cls, ch, k) + 4096;
 }
-constexpr size_t WS_TARGET = (size_t)12 << 30;  // recommended workspace cap
+constexpr size_t WS_TARGET = (size_t)40 << 30;  // recommended workspace cap (B200: 180 GB HBM3e)
 inline int64_t recommended_chunk(const Ctx& c, int cls, int64_t B, int k) {
   if (B <= 1024) return B;
   if (total_bytes(c, cls, B, k) <= WS_TARGET) return B;

@@ -126,8 +126,6 @@ __global__ void __launch_bounds__(NT) gemm_nn_tc_kernel(const float* __restrict_
   const float* abase = A + (m0 + srow) * lda + skc * 4;
   const float* bbase = Bt + hl_stride + (int64_t)(n0 + srow) * ldb + skc * 4;  // hi; lo is hl_stride further
   const int st_off = skc * LBO + (srow >> 3) * SBO + (srow & 7) * 16;   // + q * 2 * SBO per 16 rows
-  const int64_t am = m0 + tid;
-  const bool a_ok = am < M;
 
   float4 ra[KC / 4];
   auto load_chunk = [&](int k0) {

@@ -15,7 +15,7 @@ from ._cabi import NetDesc, DgmkError  # noqa: F401
 
 _WS_CACHE: dict = {}
 # cap on the scratch a single call may hold; the steps chunk the batch to fit.
-WORKSPACE_CAP_BYTES = 16 << 30
+WORKSPACE_CAP_BYTES = 48 << 30
 
 
 def _dev_f32(*tensors):
