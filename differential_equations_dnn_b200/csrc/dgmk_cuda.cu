@@ -7,6 +7,8 @@
 #include "dgmk_gemm.cuh"
 #include "dgmk_gemm_tc.cuh"
 #include "dgmk_gemm_tc_tn.cuh"
+#include "dgmk_lane_gemm.cuh"
+#include "dgmk_lane_epi.cuh"
 
 namespace dgmk {
 
@@ -17,6 +19,8 @@ constexpr int EW_THREADS = 256;
 static unsigned long long g_launches = 0;
 // GEMM engine selector for A/B measurements (dgmk_set_gemm_engine): tensor cores on by default
 static bool g_use_tc = true;
+// fused units-on-lanes kernels (GEMM + element-wise stage in one launch) where the shape allows
+static bool g_fuse = true;
 
 template <class F>
 __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const F f, int64_t n) {
@@ -140,9 +144,9 @@ struct CudaBackend {
   cudaStream_t st;
   const char* err;
   int sms;
-  bool use_tc;
+  bool use_tc, fuse;
   int64_t hl_stride = 0;  // distance between the plain / tf32-hi / tf32-lo copies of the packed weights
-  explicit CudaBackend(void* stream) : st((cudaStream_t)stream), err(nullptr), sms(148), use_tc(g_use_tc) {
+  explicit CudaBackend(void* stream) : st((cudaStream_t)stream), err(nullptr), sms(148), use_tc(g_use_tc), fuse(g_fuse) {
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) {
       int v = 0;
@@ -188,6 +192,62 @@ struct CudaBackend {
     if (BN == 128) { DGMK_NN(128) } else if (BN == 64) { DGMK_NN(64) } else { DGMK_NN(32) }
 #undef DGMK_NN
     post();
+  }
+  // ---- fused GEMM + element-wise stages (dgmk_lane_gemm.cuh): hidden size 128, channel sets
+  // whose channel count divides 8 (value, ODE/FHN, heat) ------------------------------------
+  bool lane_ok(int Hp, int cs) const {
+    return use_tc && fuse && Hp == lg::KTOT && (cs == CS_V || cs == CS_D1O1 || cs == CS_HEAT);
+  }
+  template <class EPI>
+  void lane_gemm(const float* X, int64_t ldx, const float* Wt, int64_t ldw, int64_t M, int ngates, const EPI& epi) {
+    if (M <= 0) return;
+    // opt-in shared memory size: per function and per device
+    static unsigned long long done_mask = 0;
+    int dev = 0;
+    note(cudaGetDevice(&dev));
+    if (!((done_mask >> (dev & 63)) & 1ull)) {
+      note(cudaFuncSetAttribute(lg::lane_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, lg::SMEM_BYTES));
+      done_mask |= 1ull << (dev & 63);
+    }
+    const int64_t ntiles = (M + lg::NR - 1) / lg::NR;
+    int64_t grid = ntiles * ngates < sms ? ntiles * ngates : sms;
+    grid = grid / ngates * ngates;
+    if (grid < ngates) grid = ngates;
+    lg::lane_gemm_kernel<EPI><<<(unsigned)grid, lg::NT, lg::SMEM_BYTES, st>>>(X, ldx, Wt, ldw, hl_stride, M, ngates, epi);
+    post();
+  }
+  // one DGM layer forward: [Z|G|R] GEMM + gate activations + s*R, then the H GEMM + activation +
+  // state update.  Wb = packed [4*Hp, Hp] (gate, out unit) x in unit.
+  template <class CS, int ACT>
+  void dgm_fwd_fused(const XSrc& xs, const float* S, float* A4, const F4* ub, float* SR, float* Sn, const float* Wb, int Hp,
+                     int64_t M) {
+    if constexpr (CS::C == 1 || CS::C == 2 || CS::C == 4) {
+      lg::DgmFwd1Epi<CS, ACT> e1; e1.xs = xs; e1.A4 = A4; e1.ub = ub; e1.S = S; e1.SR = SR;
+      lane_gemm(S, Hp, Wb, Hp, M, 3, e1);
+      lg::DgmFwd2Epi<CS, ACT> e2; e2.xs = xs; e2.A4 = A4; e2.ub = ub; e2.S = S; e2.Sn = Sn;
+      lane_gemm(SR, Hp, Wb + (int64_t)3 * Hp * Hp, Hp, M, 1, e2);
+    } else if (!err) err = "internal: fused path called with an unsupported channel set";
+  }
+  // (s*R)bar = abar_H W_h fused with the R-gate adjoint (DgmRev2Fn).  Wfh = packed [Hp in, Hp out]
+  template <class CS, int ACT>
+  void dgm_rev2_fused(const float* A4, const float* S, float* AB4, float* SBp, const float* Wfh, int Hp, int64_t M) {
+    if constexpr (CS::C == 1 || CS::C == 2 || CS::C == 4) {
+      lg::DgmRev2Epi<CS, ACT> e; e.A4 = A4; e.S = S; e.AB4 = AB4; e.SBp = SBp;
+      lane_gemm(AB4 + 3 * Hp, 4 * (int64_t)Hp, Wfh, Hp, M, 1, e);
+    } else if (!err) err = "internal: fused path called with an unsupported channel set";
+  }
+  // MLP hidden layer forward: GEMM + bias + activation
+  template <class CS, int ACT>
+  void mlp_fwd_fused(const float* Yp, float* G, const F4* ub, float* Yn, const float* Wb, int Hp, int64_t M) {
+    if constexpr (CS::C == 1 || CS::C == 2 || CS::C == 4) {
+      lg::MlpActEpi<CS, ACT> e; e.G = G; e.ub = ub; e.Yn = Yn;
+      lane_gemm(Yp, Hp, Wb, Hp, M, 1, e);
+    } else if (!err) err = "internal: fused path called with an unsupported channel set";
+  }
+  // C[M, Hp] = X[M, Hp] Wt[Hp, Hp]^T on the lane kernel (MLP data gradient)
+  void lane_store(const float* X, int64_t ldx, const float* Wt, float* C, int64_t ldc, int Hp, int64_t M) {
+    lg::StoreEpi<false> e; e.C = C; e.ldc = ldc;
+    lane_gemm(X, ldx, Wt, Hp, M, 1, e);
   }
   void reduce(const float* part, int nparts, int64_t n, float* out) {
     reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, nparts, n, out);
@@ -298,8 +358,9 @@ __global__ void __launch_bounds__(256) ffma_probe_kernel(float* out, const float
 
 extern "C" {
 unsigned long long dgmk_launch_count(void) { return dgmk::g_launches; }
-// 0 = FP32 FFMA2 tiles only, 1 = tcgen05 3xTF32 tiles where the shape allows (default)
-void dgmk_set_gemm_engine(int tensor_cores) { dgmk::g_use_tc = tensor_cores != 0; }
+// 0 = FP32 FFMA2 tiles only; 1 = tcgen05 3xTF32, fused GEMM + element-wise kernels where the shape
+// allows (default); 2 = tcgen05 3xTF32 streaming tiles + separate element-wise kernels
+void dgmk_set_gemm_engine(int engine) { dgmk::g_use_tc = engine != 0; dgmk::g_fuse = engine == 1; }
 // same tcgen05 tile the pipeline launches: C[M,N] = A[M,K] Bt[N,K]^T, lda = ldc = ld
 int dgmk_gemm_tc_probe(const float* A, const float* Bt, float* C, int64_t M, int N, int K, int64_t ld, void* stream) {
   if (N % 128 || K % 32) return DGMK_EINVAL;

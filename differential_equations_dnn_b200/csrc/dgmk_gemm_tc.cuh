@@ -62,6 +62,15 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
 }
+// one lane of a converged warp.  tcgen05.mma must be issued from warp-uniform control flow
+// (if (warp == 0) { if (elect_one()) ... }): under a divergent `if (tid == 0)` ptxas cannot keep
+// the descriptors in uniform registers and wraps EVERY MMA in an R2UR broadcast loop -- measured
+// ~90 cycles per MMA on the issuing thread against 64 for the MMA itself (N = 128).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
 }
@@ -73,10 +82,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// Prefetch loads must really be ISSUED where they are written: a plain __ldg is a pure read that
+// the compiler is free to sink down to its first use (it did: no load was in flight across the
+// barriers and the tiles were latency-bound).  volatile asm pins the issue point.
+__device__ __forceinline__ float4 ldg_f4_pinned(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+// round-to-nearest (ties away) to 10 explicit mantissa bits with two full-rate integer ops;
+// cvt.rna.tf32.f32 computes the same value but runs on the slow conversion pipe (measured: the
+// 32 conversions per thread per chunk cost ~1000 cycles)
 __device__ __forceinline__ float tf32_hi(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 // split a float4 into hi / lo and store both 16-byte chunks
 __device__ __forceinline__ void split_store(char* hi_base, char* lo_base, int off, float4 v) {
@@ -131,7 +149,7 @@ __global__ void __launch_bounds__(NT) gemm_nn_tc_kernel(const float* __restrict_
   auto load_chunk = [&](int k0) {
 #pragma unroll
     for (int q = 0; q < 8; ++q)
-      ra[q] = (m0 + srow + q * 16 < M) ? __ldg(reinterpret_cast<const float4*>(abase + (int64_t)q * 16 * lda + k0))
+      ra[q] = (m0 + srow + q * 16 < M) ? ldg_f4_pinned(abase + (int64_t)q * 16 * lda + k0)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
   };
   // weights: already split, straight copies (L2-resident, shared by every CTA)
@@ -186,7 +204,8 @@ __global__ void __launch_bounds__(NT) gemm_nn_tc_kernel(const float* __restrict_
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy stores -> async proxy (UMMA)
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
+      if (elect_one()) {
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const uint64_t dAh = make_desc(smem_u32(sAh)), dAl = make_desc(smem_u32(sAl));
       const uint64_t dBh = make_desc(smem_u32(sBh)), dBl = make_desc(smem_u32(sBl));
@@ -203,6 +222,8 @@ __global__ void __launch_bounds__(NT) gemm_nn_tc_kernel(const float* __restrict_
         mma_tf32(d, dAh + adv, dBh + adv, 1u);
       }
       mma_commit(bar_a + 8 * buf);
+      }
+      __syncwarp();
     }
     if (c > 0) drain(buf ^ 1);   // overlaps the MMAs just issued
   }

@@ -66,6 +66,11 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {   // see dgmk_gemm_tc.cuh
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
 }
@@ -77,10 +82,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ float4 ldg_f4_pinned(const float* p) {   // see dgmk_gemm_tc.cuh
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+// round-to-nearest (ties away) to 10 explicit mantissa bits with two full-rate integer ops;
+// cvt.rna.tf32.f32 computes the same value but runs on the slow conversion pipe (measured: the
+// 32 conversions per thread per chunk cost ~1000 cycles)
 __device__ __forceinline__ float tf32_hi(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 // split a float4 into hi / lo and store both 16-byte chunks
 __device__ __forceinline__ void split_store(char* hi_base, char* lo_base, int off, float4 v) {
@@ -202,8 +213,8 @@ __global__ void __launch_bounds__(NT) gemm_tn_tc_kernel(const float* __restrict_
     for (int q = 0; q < 4; ++q) {
       const int64_t m = m0 + q * 8 + warp;
       const bool ok = m < me;
-      ra[q] = ok ? __ldg(reinterpret_cast<const float4*>(abase + m * lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      rs[q] = ok ? __ldg(reinterpret_cast<const float4*>(sbase + m * lds)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ra[q] = ok ? ldg_f4_pinned(abase + m * lda) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rs[q] = ok ? ldg_f4_pinned(sbase + m * lds) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (do_e && tid < KC) {
       const int64_t m = m0 + tid;
@@ -239,7 +250,8 @@ __global__ void __launch_bounds__(NT) gemm_tn_tc_kernel(const float* __restrict_
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
+      if (elect_one()) {
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const uint64_t dAh = make_desc_mn(smem_u32(sAh)), dAl = make_desc_mn(smem_u32(sAl));
       const uint64_t dBh = make_desc_mn(smem_u32(sBh)), dBl = make_desc_mn(smem_u32(sBl));
@@ -256,6 +268,8 @@ __global__ void __launch_bounds__(NT) gemm_tn_tc_kernel(const float* __restrict_
         mma_tf32<IDESC_MN>(d, dAh + adv, dBh + adv, 1u);
       }
       mma_commit(bar_a + 8 * buf);
+      }
+      __syncwarp();
     }
     if (do_e) {
 #pragma unroll

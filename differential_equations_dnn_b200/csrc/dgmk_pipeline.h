@@ -176,12 +176,24 @@ struct Pipeline {
       })
       for (int l = 0; l < n.L; ++l) {
         if (!n.is_dgm()) {
+          if (bk.lane_ok(Hp, pb.cs)) {   // GEMM + bias + activation in one kernel
+            DGMK_ACT_SWITCH(n.act, ACT, {
+              bk.template mlp_fwd_fused<CS, ACT>(pb.S[l], pb.G[l], ub(l), pb.S[l + 1], c.Wp + c.pl.wb[l], Hp, M);
+            })
+            continue;
+          }
           bk.gemm_nn(pb.S[l], Hp, c.Wp + c.pl.wf[l], Hp, c.Wp + c.pl.wb[l], Hp, pb.G[l], Hp, M, Hp, Hp, false);
           DGMK_ACT_SWITCH(n.act, ACT, {
             MlpActFn<CS, ACT> f; f.G = pb.G[l]; f.ub = ub(l); f.Yn = pb.S[l + 1]; f.Hp = Hp;
             bk.ew(f, R * Hp);
           })
         } else {
+          if (bk.lane_ok(Hp, pb.cs)) {   // two kernels per layer: [Z|G|R] + s*R, then H + state update
+            DGMK_GACT_SWITCH(n.gate_act(), ACT, {
+              bk.template dgm_fwd_fused<CS, ACT>(pb.xs, pb.S[l], pb.G[l], ub(l), pb.SR[l], pb.S[l + 1], c.Wp + c.pl.wb[l], Hp, M);
+            })
+            continue;
+          }
           bk.gemm_nn(pb.S[l], Hp, c.Wp + c.pl.wf[l], 3 * Hp, c.Wp + c.pl.wb[l], Hp, pb.G[l], 4 * Hp, M, 3 * Hp, Hp, false);
           DGMK_GACT_SWITCH(n.gate_act(), ACT, {
             DgmFwd1Fn<CS, ACT> f; f.xs = pb.xs; f.A4 = pb.G[l]; f.ub = ub(l); f.S = pb.S[l]; f.SR = pb.SR[l]; f.Hp = Hp;
@@ -224,19 +236,26 @@ struct Pipeline {
           })
           // grad W = Abar^T Y_prev, and grad b (row 2 of Abar^T E) in the same pass
           bk.gemm_tn_acc(rb.AB, Hp, pb.S[l], Hp, Gp + c.pl.g_w[l], Hp, Hp, M, pb.E, Gp + c.pl.g_ub[l], Hp, c.part, c.part_n);
-          bk.gemm_nn(rb.AB, Hp, c.Wp + c.pl.wb[l], Hp, c.Wp + c.pl.wf[l], Hp, SBp, Hp, M, Hp, Hp, false);
+          if (bk.lane_ok(Hp, CS_V)) bk.lane_store(rb.AB, Hp, c.Wp + c.pl.wf[l], SBp, Hp, Hp, M);
+          else bk.gemm_nn(rb.AB, Hp, c.Wp + c.pl.wb[l], Hp, c.Wp + c.pl.wf[l], Hp, SBp, Hp, M, Hp, Hp, false);
         } else {
           DGMK_GACT_SWITCH(n.gate_act(), ACT, {
             DgmRev1Fn<CS, ACT> f; f.A4 = pb.G[l]; f.S = pb.S[l]; f.SBn = SBn; f.AB4 = rb.AB; f.SBp = SBp; f.Hp = Hp;
             bk.ew(f, R * Hp);
           })
-          // (s*R)bar = abar_H W_h
-          bk.gemm_nn(rb.AB + 3 * Hp, 4 * Hp, c.Wp + c.pl.wb[l] + (int64_t)3 * Hp * Hp, Hp, c.Wp + c.pl.wfh[l], Hp, rb.SRB, Hp, M, Hp,
-                     Hp, false);
-          DGMK_GACT_SWITCH(n.gate_act(), ACT, {
-            DgmRev2Fn<CS, ACT> f; f.A4 = pb.G[l]; f.S = pb.S[l]; f.SRB = rb.SRB; f.AB4 = rb.AB; f.SBp = SBp; f.Hp = Hp;
-            bk.ew(f, R * Hp);
-          })
+          // (s*R)bar = abar_H W_h, then the R-gate adjoint (one kernel on the fused path)
+          if (bk.lane_ok(Hp, pb.cs)) {
+            DGMK_GACT_SWITCH(n.gate_act(), ACT, {
+              bk.template dgm_rev2_fused<CS, ACT>(pb.G[l], pb.S[l], rb.AB, SBp, c.Wp + c.pl.wfh[l], Hp, M);
+            })
+          } else {
+            bk.gemm_nn(rb.AB + 3 * Hp, 4 * Hp, c.Wp + c.pl.wb[l] + (int64_t)3 * Hp * Hp, Hp, c.Wp + c.pl.wfh[l], Hp, rb.SRB, Hp, M, Hp,
+                       Hp, false);
+            DGMK_GACT_SWITCH(n.gate_act(), ACT, {
+              DgmRev2Fn<CS, ACT> f; f.A4 = pb.G[l]; f.S = pb.S[l]; f.SRB = rb.SRB; f.AB4 = rb.AB; f.SBp = SBp; f.Hp = Hp;
+              bk.ew(f, R * Hp);
+            })
+          }
           // s bar += [abar_Z | abar_G | abar_R] [W_z; W_g; W_r]
           bk.gemm_nn(rb.AB, 4 * Hp, c.Wp + c.pl.wb[l], Hp, c.Wp + c.pl.wf[l], 3 * Hp, SBp, Hp, M, Hp, 3 * Hp, true);
           // weight gradients

@@ -15,6 +15,15 @@ struct HostBackend {
   int64_t hl_stride = 0;
   explicit HostBackend(void*) {}
   template <class F> void ew(const F& f, int64_t n) { for (int64_t i = 0; i < n; ++i) f(i); }
+  // the fused GEMM + element-wise kernels are CUDA-only: the harness always takes the unfused route
+  bool lane_ok(int, int) const { return false; }
+  template <class CS, int ACT>
+  void dgm_fwd_fused(const dgmk::XSrc&, const float*, float*, const dgmk::F4*, float*, float*, const float*, int, int64_t) {}
+  template <class CS, int ACT>
+  void dgm_rev2_fused(const float*, const float*, float*, float*, const float*, int, int64_t) {}
+  template <class CS, int ACT>
+  void mlp_fwd_fused(const float*, float*, const dgmk::F4*, float*, const float*, int, int64_t) {}
+  void lane_store(const float*, int64_t, const float*, float*, int64_t, int, int64_t) {}
   void gemm_nn(const float* A, int64_t lda, const float* B, int64_t ldb, const float* Bt, int64_t ldbt, float* C, int64_t ldc, int64_t M,
                int N, int K, bool acc) {
     // both packed orientations must describe the same matrix (checks the packing tables)
