@@ -7,6 +7,7 @@
 #include "dgmk_gemm.cuh"
 #include "dgmk_gemm_tc.cuh"
 #include "dgmk_gemm_tc_tn.cuh"
+#include "dgmk_wgrad_ws.cuh"
 #include "dgmk_lane_gemm.cuh"
 #include "dgmk_lane_epi.cuh"
 
@@ -273,6 +274,43 @@ struct CudaBackend {
     int64_t rps = ((M + splits - 1) / splits + 31) / 32 * 32;
     splits = (M + rps - 1) / rps;
     float* PE = E ? part + splits * tile : nullptr;
+    // warp-specialised tcgen05 kernel (A^T through tensor memory): one CTA per SM, one wave
+    const bool ws_ok = use_tc && fuse && E && N % tc::BM == 0 && Kd % tc::BN == 0 && lds == 128 && (lda == 128 || lda == 512);
+    if (ws_ok) {
+      // CTAs: one wave; each walks `nseg` segments of seg_rows rows and emits one partial per
+      // segment, so the FP32 chains stay as short as with the many-splits streaming tile
+      const int tiles_ws = (Kd / 128) * (N / 128);
+      const int64_t per_seg = tile + 8 * (int64_t)N;    // W partial + two E partials
+      int64_t max_seg = part_n / per_seg;
+      if (max_seg > 512) max_seg = 512;
+      int64_t ctas = sms / tiles_ws;
+      if (ctas > by_rows) ctas = by_rows;
+      if (ctas > max_seg) ctas = max_seg;
+      if (ctas < 1) ctas = 1;
+      int64_t nseg = ((M + ctas - 1) / ctas + 8191) / 8192;   // segments of <= 8192 rows
+      if (nseg * ctas > max_seg) nseg = max_seg / ctas;
+      if (nseg < 1) nseg = 1;
+      const int64_t seg_rows = ((M + ctas * nseg - 1) / (ctas * nseg) + 31) / 32 * 32;
+      ctas = (M + seg_rows * nseg - 1) / (seg_rows * nseg);
+      const int64_t nparts = (M + seg_rows - 1) / seg_rows;   // segments that contain rows (the rest is never written)
+      float* PEw = part + ctas * nseg * tile;
+      dim3 gws(Kd / 128, N / 128, (unsigned)ctas);
+      static unsigned long long done_mask = 0;
+      int dev = 0;
+      note(cudaGetDevice(&dev));
+      if (!((done_mask >> (dev & 63)) & 1ull)) {
+        note(cudaFuncSetAttribute(wg::wgrad_ws_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES));
+        note(cudaFuncSetAttribute(wg::wgrad_ws_kernel<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES));
+        done_mask |= 1ull << (dev & 63);
+      }
+      if (lda == 512) wg::wgrad_ws_kernel<512, 128><<<gws, wg::NT, wg::SMEM_BYTES, st>>>(A, S, E, part, PEw, N, Kd, M, seg_rows, (int)nseg);
+      else wg::wgrad_ws_kernel<128, 128><<<gws, wg::NT, wg::SMEM_BYTES, st>>>(A, S, E, part, PEw, N, Kd, M, seg_rows, (int)nseg);
+      post();
+      reduce(part, (int)nparts, tile, out);
+      reduce_partials_2d_kernel<<<(unsigned)((4 * N + 255) / 256), 256, 0, st>>>(PEw, (int)(2 * nparts), 4, N, outE, ldoE);
+      post();
+      return;
+    }
     dim3 grid(Kd / BN, (N + GEMM_BM - 1) / GEMM_BM, (unsigned)splits);
     if (use_tc && E && N % tc::BM == 0 && Kd % tc::BN == 0) {
       static bool attr_done = false;

@@ -26,14 +26,15 @@
 // lo*hi + hi*lo then hi*hi from zero in TMEM, the four chunk results summed in round-to-nearest
 // registers.  Each chunk has its own 64 accumulator columns: TMEM = 256 (weights) + 4 x 64.
 //
-// One CTA per SM, 14 warps, decoupled by mbarriers:
+// One CTA per SM, 16 warps (4 warpgroups), decoupled by mbarriers:
 //   warp 0       bulk-copy producer: cp.async.bulk (TMA engine; rows are contiguous, no tensor map
 //                needed) of the next [64 x 128] FP32 row tile into a 3-deep raw ring
-//   warps 2-5    transform: raw tile -> tf32 hi / lo -> UMMA canonical K-major operand tile (2-deep)
+//   warps 4-7    transform: raw tile -> tf32 hi / lo -> UMMA canonical K-major operand tile (2-deep)
 //   warp 1       MMA issuer: per K chunk 12 tcgen05.mma (A = weights in TMEM, B = rows in smem,
 //                M=128, N=64, K=8) -> tcgen05.commit per chunk; frees the operand tile at the end
-//   warps 6-13   epilogue: tcgen05.ld each chunk result as soon as it is complete (handing its
-//                columns straight back to the MMA warp), add, then run the fused stage (EPI)
+//   warps 8-15   epilogue: tcgen05.ld each chunk result as soon as it is complete (handing its
+//                columns straight back to the MMA warp), add, then run the fused stage (EPI);
+//                setmaxnreg moves the producers' spare registers to these two warpgroups
 // CTA b works on gate b % ngates for its whole life (weight-stationary); the CTAs of the different
 // gates walk the same row tiles at the same time and share them in L2.
 #pragma once
@@ -75,7 +76,11 @@ constexpr int X_OFF = RAW_OFF + RAW_STAGES * RAW_BYTES;
 constexpr int BAR_OFF = X_OFF + X_STAGES * X_STAGE_BYTES;
 constexpr int SMEM_BYTES = BAR_OFF + 192;
 constexpr int NTW = 4;                // transform warps
-constexpr int NT = 14 * 32;
+// warp roles, aligned to warpgroups so that registers can be moved between them (setmaxnreg):
+//   WG0: warp 0 copy, warp 1 MMA, warps 2-3 idle | WG1: warps 4-7 transform | WG2-3: warps 8-15 epilogue
+constexpr int W_TRANSFORM = 4, W_EPI = 8;
+constexpr int NT = 16 * 32;
+constexpr int REGS_PRODUCER = 56, REGS_EPI = 200;   // 8 warps x 32 x 56 + 8 warps x 32 x 200 = 64 K registers
 constexpr int NCONS = 8 * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int TM_WHI = 0, TM_WLO = KTOT, TM_ACC = 2 * KTOT;   // TMEM column map
@@ -204,10 +209,10 @@ __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restric
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
-  if (warp >= 6) {
+  if (warp >= W_EPI) {
     // resident weights of this gate -> TMEM: lane = unit, column = k (32-bit cells); the first four
     // epilogue warps write the tf32-hi copy, the other four the lo copy
-    const int quarter = warp & 3, half = (warp - 6) >> 2;
+    const int quarter = warp & 3, half = (warp - W_EPI) >> 2;
     const float* src = Wt + (1 + half) * hl_stride + (int64_t)(gate * NU + quarter * 32 + lane) * ldw;
     const uint32_t tw = tmem + ((uint32_t)(quarter * 32) << 16) + (half ? TM_WLO : TM_WHI);
 #pragma unroll 1
@@ -223,7 +228,12 @@ __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restric
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 
+  // The epilogue warps hold the prefetch ring and the accumulators: setmaxnreg (one per warpgroup,
+  // at the top of its role branch so that ptxas allocates each branch against its own limit) gives
+  // them the registers the copy / MMA / transform warps do not need.
   if (blockIdx.x < ngrp * ngates) {
+   if (warp < W_TRANSFORM) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS_PRODUCER));
     if (warp == 0) {
       // ================================ bulk-copy producer ================================
       uint32_t i = 0, rs = 0, use = 0;
@@ -293,9 +303,12 @@ __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restric
         }
       }
       LG_PROF_OUT(8);
-    } else if (warp < 2 + NTW) {
+    }
+   } else if (warp < W_EPI) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS_PRODUCER));
+    {
       // ================================ transform ==========================================
-      const int ttid = tid - 64;
+      const int ttid = tid - W_TRANSFORM * 32;
       const int piece = ttid & 7, rbase = ttid >> 3;   // rows rbase + 16 q
       const int st_off = piece * X_LBO + (rbase >> 3) * SBO + (rbase & 7) * 16;   // + q * 2 * SBO
       uint32_t i = 0, rs = 0, use = 0;
@@ -329,21 +342,33 @@ __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restric
         LG_ADD(2, t2);
         if (++rs == RAW_STAGES) { rs = 0; ++use; }
       }
-      if (warp == 2) { LG_PROF_OUT(16); }
-    } else {
+      if (warp == W_TRANSFORM) { LG_PROF_OUT(16); }
+    }
+   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REGS_EPI));
+    {
       // ================================ epilogue ===========================================
-      const int quarter = warp & 3, half = (warp - 6) >> 2;
+      const int quarter = warp & 3, half = (warp - W_EPI) >> 2;
       const int j = quarter * 32 + lane;
       const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + TM_ACC + half * 32;
       const typename EPI::Const ek = epi.init(gate, j);
+      // The global loads of a group are issued TWO groups (16 rows) ahead of their use, across tile
+      // boundaries: pre[cg] belongs to group cg of the current tile; while group cg is computed the
+      // loads of group cg+2 (or of group cg-2 of the next tile) go out.
+      typename EPI::Tile et, et_next;
+      typename EPI::Pre pre[4];
       uint32_t i = 0;
       LG_PROF_DECL;
+      if (grp < ntiles) {
+        const int64_t r0 = grp * NR + half * 32;
+        epi.tile(et, ek, r0, M, lane);
+        epi.prefetch(pre[0], et, ek, r0, 0, M);
+        epi.prefetch(pre[1], et, ek, r0 + 8, 1, M);
+      }
       for (int64_t t = grp; t < ntiles; t += ngrp, ++i) {
         const int64_t row0 = t * NR + half * 32;
-        typename EPI::Tile et;
-        typename EPI::Pre pre[2];
-        epi.tile(et, ek, row0, M, lane);
-        epi.prefetch(pre[0], et, ek, row0, 0, M);   // in flight while the tile's MMAs run
+        const int64_t nrow0 = (t + ngrp) * NR + half * 32;
+        const bool has_next = t + ngrp < ntiles;
         float a[32];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
@@ -372,14 +397,21 @@ __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restric
         LG_T(t2);
 #pragma unroll
         for (int cg = 0; cg < 4; ++cg) {
-          if (cg < 3) epi.prefetch(pre[(cg + 1) & 1], et, ek, row0 + (cg + 1) * 8, cg + 1, M);   // next group's loads first
+          if (cg < 2) {
+            epi.prefetch(pre[cg + 2], et, ek, row0 + (cg + 2) * 8, cg + 2, M);
+          } else if (has_next) {
+            if (cg == 2) epi.tile(et_next, ek, nrow0, M, lane);
+            epi.prefetch(pre[cg - 2], et_next, ek, nrow0 + (cg - 2) * 8, cg - 2, M);
+          }
           const float a8[8] = {a[cg * 8], a[cg * 8 + 1], a[cg * 8 + 2], a[cg * 8 + 3], a[cg * 8 + 4], a[cg * 8 + 5], a[cg * 8 + 6], a[cg * 8 + 7]};
-          epi.apply(pre[cg & 1], ek, row0 + cg * 8, M, a8);
+          epi.apply(pre[cg], ek, row0 + cg * 8, M, a8);
         }
+        et = et_next;
         LG_ADD(2, t2);
       }
-      if (warp == 6) { LG_PROF_OUT(24); }
+      if (warp == W_EPI) { LG_PROF_OUT(24); }
     }
+   }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();

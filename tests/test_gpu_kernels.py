@@ -192,10 +192,12 @@ def test_vs_oracle_midsize(K):
 
 @pytest.mark.parametrize("kind,prob", [("dgm", "heat"), ("mlp", "heat"), ("dgm", "fhn"), ("mlp", "ode128")])
 def test_engines_agree(K, kind, prob):
-    """The fused units-on-lanes kernels (engine 1), the streaming tcgen05 tiles + separate element-wise
-    kernels (engine 2) and the FP32 FFMA2 tiles (engine 0) compute the same step: ragged row counts
-    (not a multiple of the 64-row tile), hidden size 128."""
+    """The fused units-on-lanes kernels + warp-specialised weight gradient (engine 1), the streaming
+    tcgen05 tiles + separate element-wise kernels (engine 2) and the FP32 FFMA2 tiles (engine 0)
+    compute the same step: each within the parity bar of the FP64 jet oracle, per tensor, on ragged
+    row counts (not a multiple of the 64-row tile) at hidden size 128."""
     from differential_equations_dnn_b200 import _cabi, dgm_net, neural_networks
+    from oracle import jets_np
     lib = _cabi.load()
     torch.manual_seed(7)
     B = 3000 + 37
@@ -203,30 +205,29 @@ def test_engines_agree(K, kind, prob):
     if prob == "heat":
         net = (dgm_net.DGM(2, 1, 128, 2) if kind == "dgm" else neural_networks.MLP(2, 1, 128, 2, activation="tanh")).cuda()
         x = torch.pi * torch.rand([B, 1], generator=gen); t = 3.0 * torch.rand([B, 1], generator=gen); z = torch.zeros(B, 1)
-        args = [a.cuda() for a in (torch.cat([x, t], 1), torch.cat([x, z], 1), torch.cat([z, t], 1),
-                                   torch.cat([z + torch.pi, t], 1), z, z.clone())]
-        step = lambda: K.heat_step(net.desc, net.flat_theta(), *args).clone()
+        host = [torch.cat([x, t], 1), torch.cat([x, z], 1), torch.cat([z, t], 1), torch.cat([z + torch.pi, t], 1), z, z.clone()]
+        fn, ofn = K.heat_step, jets_np.heat_step
     elif prob == "fhn":
         net = dgm_net.DGM(1, 2, 128, 2).cuda()
-        t = 30.01 * torch.rand([B, 1], generator=gen)
-        args = [t.cuda(), torch.zeros(B, 1).cuda(), torch.zeros(B, 2).cuda()]
-        step = lambda: K.fhn_step(net.desc, net.flat_theta(), *args).clone()
+        host = [30.01 * torch.rand([B, 1], generator=gen), torch.zeros(B, 1), torch.zeros(B, 2)]
+        fn, ofn = K.fhn_step, jets_np.fhn_step
     else:
         net = neural_networks.MLP(1, 1, 128, 2, activation="sigmoid").cuda()
-        t = 1.01 * torch.rand([B, 1], generator=gen)
-        args = [t.cuda(), torch.zeros(B, 1).cuda(), 2.0 * torch.ones(B, 1).cuda()]
-        step = lambda: K.ode_step(net.desc, net.flat_theta(), *args).clone()
+        host = [1.01 * torch.rand([B, 1], generator=gen), torch.zeros(B, 1), 2.0 * torch.ones(B, 1)]
+        fn, ofn = K.ode_step, jets_np.ode_step
+    args = [a.cuda() for a in host]
+    d = net.desc
+    spec = np.array([d.kind, d.input_dim, d.output_dim, d.hidden_size, d.num_layers, d.activation])
+    lo, go = ofn(spec, net.flat_theta().double().cpu().numpy(), *[a.double().numpy() for a in host])
     try:
         out = {}
         for eng in (0, 2, 1):
             lib.dgmk_set_gemm_engine(eng)
-            out[eng] = step().double().cpu().numpy()
+            out[eng] = fn(d, net.flat_theta(), *args).double().cpu().numpy()
     finally:
         lib.dgmk_set_gemm_engine(1)
-    for (_, off, n, live) in net.param_slices():
-        if not live:
-            continue
-        a1, a2, a0 = out[1][off:off + n], out[2][off:off + n], out[0][off:off + n]
-        assert rel(a1, a2) < 2e-6, ("fused vs streaming", rel(a1, a2))
-        assert rel(a1, a0) < 2e-5, ("fused vs ffma", rel(a1, a0))
-    assert abs(out[1][-1] - out[0][-1]) <= 2e-6 * abs(out[0][-1])
+    for eng in (0, 2, 1):
+        assert abs(out[eng][-1] - lo) <= TOL * abs(lo), (eng, out[eng][-1], lo)
+        for (_, off, n, live) in net.param_slices():
+            if live and np.linalg.norm(go[off:off + n]) > 0:
+                assert rel(out[eng][off:off + n], go[off:off + n]) < TOL, (eng, off, rel(out[eng][off:off + n], go[off:off + n]))
