@@ -65,7 +65,10 @@ __device__ __forceinline__ void add_input_map_xy(float* a, const F4& u, float x0
   add_input_map<CS>(a, u, x, d);
 }
 // row index clamped into [0, M): loads of the padding rows of the last tile stay in bounds
-__device__ __forceinline__ int64_t clampr(int64_t r, int64_t M) { return r < M ? r : M - 1; }
+// (FULL: the whole half tile lies inside [0, M) -- no clamps, no store predicates, and every address
+// of the tile folds into one base register plus immediates)
+template <bool FULL>
+__device__ __forceinline__ int64_t clampr(int64_t r, int64_t M) { return (FULL || r < M) ? r : M - 1; }
 
 // Z, G, R = act(W s + U x + b) -> a-form; SR = s * R        (dgm_net.py:63-65)
 template <class CS, int ACT>
@@ -77,13 +80,15 @@ struct DgmFwd1Epi {
   struct Pre { XPre<C> x; float s[8]; };
   __device__ __forceinline__ Const init(int gate, int j) const { Const k; k.u = ub[gate * HP + j]; k.gate = gate; k.j = j; return k; }
   __device__ __forceinline__ void tile(Tile& t, const Const&, int64_t row0, int64_t M, int lane) const { t.load(xs, row0, M, lane); }
+  template <bool FULL>
   __device__ __forceinline__ void prefetch(Pre& p, const Tile& t, const Const& k, int64_t row0, int cg, int64_t M) const {
     p.x.load(t, cg);
     if (k.gate == 2) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) p.s[q] = ldg_f(S + clampr(row0 + q, M) * HP + k.j);
+      for (int q = 0; q < 8; ++q) p.s[q] = ldg_f(S + clampr<FULL>(row0 + q, M) * HP + k.j);
     }
   }
+  template <bool FULL>
   __device__ __forceinline__ void apply(const Pre& p, const Const& k, int64_t row0, int64_t M, const float (&acc)[8]) const {
     float af[8], sr[8];   // a-form rows and (R gate) s*R rows of the whole group
 #pragma unroll
@@ -108,12 +113,12 @@ struct DgmFwd1Epi {
     float* ag = A4 + row0 * LD4 + k.gate * HP + k.j;
 #pragma unroll
     for (int q = 0; q < 8; ++q)
-      if (row0 + q < M) ag[q * LD4] = af[q];
+      if (FULL || row0 + q < M) ag[q * LD4] = af[q];
     if (k.gate == 2) {
       float* so = SR + row0 * HP + k.j;
 #pragma unroll
       for (int q = 0; q < 8; ++q)
-        if (row0 + q < M) so[q * HP] = sr[q];
+        if (FULL || row0 + q < M) so[q * HP] = sr[q];
     }
   }
 };
@@ -128,17 +133,19 @@ struct DgmFwd2Epi {
   struct Pre { XPre<C> x; float z[8], g[8], s[8]; };
   __device__ __forceinline__ Const init(int, int j) const { Const k; k.u = ub[3 * HP + j]; k.j = j; return k; }
   __device__ __forceinline__ void tile(Tile& t, const Const&, int64_t row0, int64_t M, int lane) const { t.load(xs, row0, M, lane); }
+  template <bool FULL>
   __device__ __forceinline__ void prefetch(Pre& p, const Tile& t, const Const& k, int64_t row0, int cg, int64_t M) const {
     p.x.load(t, cg);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const int64_t r = clampr(row0 + q, M);
+      const int64_t r = clampr<FULL>(row0 + q, M);
       const float* row = A4 + r * LD4 + k.j;
       p.z[q] = ldg_f(row);
       p.g[q] = ldg_f(row + HP);
       p.s[q] = ldg_f(S + r * HP + k.j);
     }
   }
+  template <bool FULL>
   __device__ __forceinline__ void apply(const Pre& p, const Const& k, int64_t row0, int64_t M, const float (&acc)[8]) const {
     float af[8], sn[8];
 #pragma unroll
@@ -165,7 +172,7 @@ struct DgmFwd2Epi {
     float* so = Sn + row0 * HP + k.j;
 #pragma unroll
     for (int q = 0; q < 8; ++q)
-      if (row0 + q < M) { row[q * LD4] = af[q]; so[q * HP] = sn[q]; }
+      if (FULL || row0 + q < M) { row[q * LD4] = af[q]; so[q * HP] = sn[q]; }
   }
 };
 
@@ -179,7 +186,9 @@ struct MlpActEpi {
   struct Pre {};
   __device__ __forceinline__ Const init(int, int j) const { Const k; k.b = ub[j].z; k.j = j; return k; }
   __device__ __forceinline__ void tile(Tile&, const Const&, int64_t, int64_t, int) const {}
+  template <bool FULL>
   __device__ __forceinline__ void prefetch(Pre&, const Tile&, const Const&, int64_t, int, int64_t) const {}
+  template <bool FULL>
   __device__ __forceinline__ void apply(const Pre&, const Const& k, int64_t row0, int64_t M, const float (&acc)[8]) const {
     float af[8], yo[8];
 #pragma unroll
@@ -199,7 +208,7 @@ struct MlpActEpi {
     float* y = Yn + row0 * HP + k.j;
 #pragma unroll
     for (int q = 0; q < 8; ++q)
-      if (row0 + q < M) { g[q * HP] = af[q]; y[q * HP] = yo[q]; }
+      if (FULL || row0 + q < M) { g[q * HP] = af[q]; y[q * HP] = yo[q]; }
   }
 };
 
@@ -214,15 +223,17 @@ struct DgmRev2Epi {
   struct Pre { float afr[8], s[8], sbar[8]; };
   __device__ __forceinline__ Const init(int, int j) const { Const k; k.j = j; return k; }
   __device__ __forceinline__ void tile(Tile&, const Const&, int64_t, int64_t, int) const {}
+  template <bool FULL>
   __device__ __forceinline__ void prefetch(Pre& p, const Tile&, const Const& k, int64_t row0, int, int64_t M) const {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const int64_t r = clampr(row0 + q, M);
+      const int64_t r = clampr<FULL>(row0 + q, M);
       p.afr[q] = ldg_f(A4 + r * LD4 + 2 * HP + k.j);
       p.s[q] = ldg_f(S + r * HP + k.j);
       p.sbar[q] = SBp[r * HP + k.j];   // read-modify-write by this thread only
     }
   }
+  template <bool FULL>
   __device__ __forceinline__ void apply(const Pre& p, const Const& k, int64_t row0, int64_t M, const float (&acc)[8]) const {
     float abo[8], sbo[8];
 #pragma unroll
@@ -244,7 +255,7 @@ struct DgmRev2Epi {
     float* so = SBp + row0 * HP + k.j;
 #pragma unroll
     for (int q = 0; q < 8; ++q)
-      if (row0 + q < M) { orow[q * LD4] = abo[q]; so[q * HP] = sbo[q]; }
+      if (FULL || row0 + q < M) { orow[q * LD4] = abo[q]; so[q * HP] = sbo[q]; }
   }
 };
 

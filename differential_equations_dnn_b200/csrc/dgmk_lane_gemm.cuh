@@ -144,6 +144,8 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float4 (&v)[8]) 
       : "memory");
 }
 
+template <bool B> struct FullTag { static constexpr bool value = B; };
+
 // ---- plain epilogue: C[r, gate*128 + j] (+)= D[j, r]  (interface: see dgmk_lane_epi.cuh) --------
 template <bool ACCUM>
 struct StoreEpi {
@@ -153,18 +155,20 @@ struct StoreEpi {
   struct Pre { float old[8]; };
   __device__ __forceinline__ Const init(int gate, int j) const { Const k; k.col = gate * NU + j; return k; }
   __device__ __forceinline__ void tile(Tile&, const Const&, int64_t, int64_t, int) const {}
+  template <bool FULL>
   __device__ __forceinline__ void prefetch(Pre& p, const Tile&, const Const& k, int64_t row0, int, int64_t M) const {
     if (ACCUM) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) p.old[q] = (row0 + q < M) ? C[(row0 + q) * ldc + k.col] : 0.f;
+      for (int q = 0; q < 8; ++q) p.old[q] = (FULL || row0 + q < M) ? C[(row0 + q) * ldc + k.col] : 0.f;
     }
   }
   // a[q] = D[j, row0 + q], q = 0..7; rows >= M are padding
+  template <bool FULL>
   __device__ __forceinline__ void apply(const Pre& p, const Const& k, int64_t row0, int64_t M, const float (&a)[8]) const {
     float* c = C + row0 * ldc + k.col;
 #pragma unroll
     for (int q = 0; q < 8; ++q)
-      if (row0 + q < M) c[q * ldc] = ACCUM ? p.old[q] + a[q] : a[q];
+      if (FULL || row0 + q < M) c[q * ldc] = ACCUM ? p.old[q] + a[q] : a[q];
   }
 };
 
@@ -362,8 +366,8 @@ __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restric
       if (grp < ntiles) {
         const int64_t r0 = grp * NR + half * 32;
         epi.tile(et, ek, r0, M, lane);
-        epi.prefetch(pre[0], et, ek, r0, 0, M);
-        epi.prefetch(pre[1], et, ek, r0 + 8, 1, M);
+        epi.template prefetch<false>(pre[0], et, ek, r0, 0, M);
+        epi.template prefetch<false>(pre[1], et, ek, r0 + 8, 1, M);
       }
       for (int64_t t = grp; t < ntiles; t += ngrp, ++i) {
         const int64_t row0 = t * NR + half * 32;
@@ -395,17 +399,23 @@ __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restric
           LG_ADD(1, t1);
         }
         LG_T(t2);
+        // fast path: this half tile and the next one lie inside [0, M): no clamps, no predicates
+        auto groups = [&](auto full_tag) {
+          constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
-        for (int cg = 0; cg < 4; ++cg) {
-          if (cg < 2) {
-            epi.prefetch(pre[cg + 2], et, ek, row0 + (cg + 2) * 8, cg + 2, M);
-          } else if (has_next) {
-            if (cg == 2) epi.tile(et_next, ek, nrow0, M, lane);
-            epi.prefetch(pre[cg - 2], et_next, ek, nrow0 + (cg - 2) * 8, cg - 2, M);
+          for (int cg = 0; cg < 4; ++cg) {
+            if (cg < 2) {
+              epi.template prefetch<FULL>(pre[cg + 2], et, ek, row0 + (cg + 2) * 8, cg + 2, M);
+            } else if (has_next) {
+              if (cg == 2) epi.tile(et_next, ek, nrow0, M, lane);
+              epi.template prefetch<FULL>(pre[cg - 2], et_next, ek, nrow0 + (cg - 2) * 8, cg - 2, M);
+            }
+            const float a8[8] = {a[cg * 8], a[cg * 8 + 1], a[cg * 8 + 2], a[cg * 8 + 3], a[cg * 8 + 4], a[cg * 8 + 5], a[cg * 8 + 6], a[cg * 8 + 7]};
+            epi.template apply<FULL>(pre[cg], ek, row0 + cg * 8, M, a8);
           }
-          const float a8[8] = {a[cg * 8], a[cg * 8 + 1], a[cg * 8 + 2], a[cg * 8 + 3], a[cg * 8 + 4], a[cg * 8 + 5], a[cg * 8 + 6], a[cg * 8 + 7]};
-          epi.apply(pre[cg], ek, row0 + cg * 8, M, a8);
-        }
+        };
+        if (row0 + 32 <= M && (!has_next || nrow0 + 32 <= M)) groups(FullTag<true>{});
+        else groups(FullTag<false>{});
         et = et_next;
         LG_ADD(2, t2);
       }
