@@ -4,7 +4,7 @@
 // GEMM rows = 8 / C collocation points with all their channels.
 //
 //   Const  init(gate, j)                          per-thread constants (input-map weights)
-//   void   tile(t, k, row0, M, lane)              once per 32-row half tile (point coordinates)
+//   void   tile(t, k, row0, M, lane)              once per tile: coordinates of the thread's EPI_ROWS rows
 //   void   prefetch(pre, t, k, row0, cg, M)       ISSUE every global load group cg needs
 //   void   apply(pre, k, row0, M, acc)            acc[q] = W[j,:] . X[row0 + q,:]; math + stores
 //
@@ -18,6 +18,7 @@
 // paths agree to the last bit given the same GEMM result.
 #pragma once
 #include "dgmk_ops.h"
+#include "dgmk_lane_gemm.cuh"
 
 namespace dgmk {
 namespace lg {
@@ -27,7 +28,7 @@ constexpr int64_t LD4 = 4 * HP;      // row pitch of the [M, 4*Hp] a-form / cota
 
 __device__ __forceinline__ float ldg_f(const float* p) { return __ldg(p); }
 
-// Coordinates of the points of a warp's 32-row half tile.  Lane l fetches point l once per tile
+// Coordinates of the points of a warp's EPI_ROWS rows of the tile.  Lane l fetches point l once per tile
 // (one XSrc::at -- an integer division -- per lane instead of one per point and lane); the groups
 // then pick their points up by shuffle.
 template <int C>
@@ -36,7 +37,7 @@ struct XTile {
   __device__ __forceinline__ void load(const XSrc& xs, int64_t row0, int64_t M, int lane) {
     x0 = 0.f; x1 = 0.f;
     const int64_t r = row0 + (int64_t)lane * C;
-    if (lane < 32 / C && r < M) {
+    if (lane < EPI_ROWS / C && r < M) {
       const float* x = xs.at(r / C);
       x0 = ldg_f(x);
       if (xs.d > 1) x1 = ldg_f(x + 1);

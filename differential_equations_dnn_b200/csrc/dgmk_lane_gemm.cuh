@@ -26,15 +26,16 @@
 // lo*hi + hi*lo then hi*hi from zero in TMEM, the four chunk results summed in round-to-nearest
 // registers.  Each chunk has its own 64 accumulator columns: TMEM = 256 (weights) + 4 x 64.
 //
-// One CTA per SM, 16 warps (4 warpgroups), decoupled by mbarriers:
+// One CTA per SM, 24 warps (6 warpgroups), decoupled by mbarriers:
 //   warp 0       bulk-copy producer: cp.async.bulk (TMA engine; rows are contiguous, no tensor map
 //                needed) of the next [64 x 128] FP32 row tile into a 3-deep raw ring
 //   warps 4-7    transform: raw tile -> tf32 hi / lo -> UMMA canonical K-major operand tile (2-deep)
 //   warp 1       MMA issuer: per K chunk 12 tcgen05.mma (A = weights in TMEM, B = rows in smem,
 //                M=128, N=64, K=8) -> tcgen05.commit per chunk; frees the operand tile at the end
-//   warps 8-15   epilogue: tcgen05.ld each chunk result as soon as it is complete (handing its
-//                columns straight back to the MMA warp), add, then run the fused stage (EPI);
-//                setmaxnreg moves the producers' spare registers to these two warpgroups
+//   warps 8-23   epilogue (warp w: TMEM lanes 32*(w%4).., 16 of the tile's 64 rows): tcgen05.ld each
+//                chunk result as soon as it is complete (handing its columns straight back to the
+//                MMA warp), add, then run the fused stage (EPI); setmaxnreg moves the producers'
+//                spare registers to these four warpgroups
 // CTA b works on gate b % ngates for its whole life (weight-stationary); the CTAs of the different
 // gates walk the same row tiles at the same time and share them in L2.
 #pragma once
@@ -79,9 +80,12 @@ constexpr int NTW = 4;                // transform warps
 // warp roles, aligned to warpgroups so that registers can be moved between them (setmaxnreg):
 //   WG0: warp 0 copy, warp 1 MMA, warps 2-3 idle | WG1: warps 4-7 transform | WG2-3: warps 8-15 epilogue
 constexpr int W_TRANSFORM = 4, W_EPI = 8;
-constexpr int NT = 16 * 32;
-constexpr int REGS_PRODUCER = 56, REGS_EPI = 200;   // 8 warps x 32 x 56 + 8 warps x 32 x 200 = 64 K registers
-constexpr int NCONS = 8 * 32;
+constexpr int EPI_WARPS = 16;                        // 4 per scheduler: the fused stages are latency-bound
+constexpr int EPI_ROWS = NR / (EPI_WARPS / 4);       // accumulator columns (= rows) per epilogue thread
+constexpr int EPI_GROUPS = EPI_ROWS / 8;
+constexpr int NT = (W_EPI + EPI_WARPS) * 32;
+constexpr int REGS_PRODUCER = 40, REGS_EPI = 96;     // must fit the launch allocation (768 x 80): 256 x 40 + 512 x 96 = 59392
+constexpr int NCONS = EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int TM_WHI = 0, TM_WLO = KTOT, TM_ACC = 2 * KTOT;   // TMEM column map
 
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restric
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
-  if (warp >= W_EPI) {
+  if (warp >= W_EPI && warp < W_EPI + 8) {
     // resident weights of this gate -> TMEM: lane = unit, column = k (32-bit cells); the first four
     // epilogue warps write the tf32-hi copy, the other four the lo copy
     const int quarter = warp & 3, half = (warp - W_EPI) >> 2;
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restric
         tc::mbar_wait(OP_FULL + 8 * ts, (i >> 1) & 1);
         LG_ADD(1, t1);
         const uint32_t xb = tc::smem_u32(smem + X_OFF + ts * X_STAGE_BYTES);
-#pragma unroll
+#pragma unroll 1   // this warp lives on 40 registers (setmaxnreg): one chunk's descriptors at a time
         for (int c = 0; c < NCH; ++c) {
           LG_T(t0);
           tc::mbar_wait(TC_EMPTY + 8 * c, (i & 1) ^ 1);   // epilogue has read the previous tile's chunk c
@@ -328,7 +332,7 @@ __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restric
         LG_T(t2);
         const char* raw = smem + RAW_OFF + rs * RAW_BYTES + rbase * (KTOT * 4) + piece * 16;
         char* xt = smem + X_OFF + ts * X_STAGE_BYTES;
-#pragma unroll
+#pragma unroll 1   // 40 registers per thread here (setmaxnreg): four 16-byte pieces in flight
         for (int c = 0; c < NCH; ++c) {
           float4 v[4];
 #pragma unroll
@@ -352,28 +356,29 @@ __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restric
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REGS_EPI));
     {
       // ================================ epilogue ===========================================
-      const int quarter = warp & 3, half = (warp - W_EPI) >> 2;
+      const int quarter = warp & 3, part = (warp - W_EPI) >> 2;
       const int j = quarter * 32 + lane;
-      const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + TM_ACC + half * 32;
+      const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + TM_ACC + part * EPI_ROWS;
       const typename EPI::Const ek = epi.init(gate, j);
-      // The global loads of a group are issued TWO groups (16 rows) ahead of their use, across tile
-      // boundaries: pre[cg] belongs to group cg of the current tile; while group cg is computed the
-      // loads of group cg+2 (or of group cg-2 of the next tile) go out.
+      // The global loads of a group (8 rows) are issued one group ahead of their use, across tile
+      // boundaries: pre[cg] belongs to group cg of the current tile; while group 0 is computed the
+      // loads of group 1 go out, while group 1 is computed those of the next tile's group 0.
       typename EPI::Tile et, et_next;
-      typename EPI::Pre pre[4];
+      typename EPI::Pre pre[EPI_GROUPS];
       uint32_t i = 0;
       LG_PROF_DECL;
       if (grp < ntiles) {
-        const int64_t r0 = grp * NR + half * 32;
+        const int64_t r0 = grp * NR + part * EPI_ROWS;
         epi.tile(et, ek, r0, M, lane);
         epi.template prefetch<false>(pre[0], et, ek, r0, 0, M);
-        epi.template prefetch<false>(pre[1], et, ek, r0 + 8, 1, M);
       }
       for (int64_t t = grp; t < ntiles; t += ngrp, ++i) {
-        const int64_t row0 = t * NR + half * 32;
-        const int64_t nrow0 = (t + ngrp) * NR + half * 32;
+        const int64_t row0 = t * NR + part * EPI_ROWS;
+        const int64_t nrow0 = (t + ngrp) * NR + part * EPI_ROWS;
         const bool has_next = t + ngrp < ntiles;
-        float a[32];
+        // the next tile's point coordinates: fetched a whole tile before their first use (a shuffle)
+        if (has_next) epi.tile(et_next, ek, nrow0, M, lane);
+        float a[EPI_ROWS];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           LG_T(t0);
@@ -381,40 +386,35 @@ __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restric
           LG_ADD(0, t0);
           LG_T(t1);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          uint32_t v0[8], v1[8], v2[8], v3[8];
-          tmem_ld8(tbase + c * NR, v0);
-          tmem_ld8(tbase + c * NR + 8, v1);
-          tmem_ld8(tbase + c * NR + 16, v2);
-          tmem_ld8(tbase + c * NR + 24, v3);
+          uint32_t v[EPI_GROUPS][8];
+#pragma unroll
+          for (int g = 0; g < EPI_GROUPS; ++g) tmem_ld8(tbase + c * NR + g * 8, v[g]);
           asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
           asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
           mbar_arrive(TC_EMPTY + 8 * c);   // these columns can take the next tile's chunk
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            a[q] = (c == 0) ? __uint_as_float(v0[q]) : a[q] + __uint_as_float(v0[q]);
-            a[8 + q] = (c == 0) ? __uint_as_float(v1[q]) : a[8 + q] + __uint_as_float(v1[q]);
-            a[16 + q] = (c == 0) ? __uint_as_float(v2[q]) : a[16 + q] + __uint_as_float(v2[q]);
-            a[24 + q] = (c == 0) ? __uint_as_float(v3[q]) : a[24 + q] + __uint_as_float(v3[q]);
-          }
+          for (int g = 0; g < EPI_GROUPS; ++g)
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              a[g * 8 + q] = (c == 0) ? __uint_as_float(v[g][q]) : a[g * 8 + q] + __uint_as_float(v[g][q]);
           LG_ADD(1, t1);
         }
         LG_T(t2);
-        // fast path: this half tile and the next one lie inside [0, M): no clamps, no predicates
+        // fast path: this part of the tile and of the next one lie inside [0, M): no clamps, no predicates
         auto groups = [&](auto full_tag) {
           constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
-          for (int cg = 0; cg < 4; ++cg) {
-            if (cg < 2) {
-              epi.template prefetch<FULL>(pre[cg + 2], et, ek, row0 + (cg + 2) * 8, cg + 2, M);
+          for (int cg = 0; cg < EPI_GROUPS; ++cg) {
+            if (cg + 1 < EPI_GROUPS) {
+              epi.template prefetch<FULL>(pre[cg + 1], et, ek, row0 + (cg + 1) * 8, cg + 1, M);
             } else if (has_next) {
-              if (cg == 2) epi.tile(et_next, ek, nrow0, M, lane);
-              epi.template prefetch<FULL>(pre[cg - 2], et_next, ek, nrow0 + (cg - 2) * 8, cg - 2, M);
+              epi.template prefetch<FULL>(pre[0], et_next, ek, nrow0, 0, M);
             }
             const float a8[8] = {a[cg * 8], a[cg * 8 + 1], a[cg * 8 + 2], a[cg * 8 + 3], a[cg * 8 + 4], a[cg * 8 + 5], a[cg * 8 + 6], a[cg * 8 + 7]};
             epi.template apply<FULL>(pre[cg], ek, row0 + cg * 8, M, a8);
           }
         };
-        if (row0 + 32 <= M && (!has_next || nrow0 + 32 <= M)) groups(FullTag<true>{});
+        if (row0 + EPI_ROWS <= M && (!has_next || nrow0 + EPI_ROWS <= M)) groups(FullTag<true>{});
         else groups(FullTag<false>{});
         et = et_next;
         LG_ADD(2, t2);

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include "../../differential_equations_dnn_b200/csrc/dgmk_gemm_tc.cuh"
 #include "../../differential_equations_dnn_b200/csrc/dgmk_lane_gemm.cuh"
+#include "../../differential_equations_dnn_b200/csrc/dgmk_lane_epi.cuh"
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
 __global__ void naive_nt(const float* A, int64_t lda, const float* Bt, int64_t ldb, float* C, int64_t ldc, int64_t M, int N, int K, bool accum) {
@@ -32,6 +33,10 @@ template <typename F> float time_ms(F f, int reps) {
   float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); return ms / reps;
 }
 using namespace dgmk;
+static XSrc xsrc1(const float* p, int64_t rows, int d) {
+  XSrc x; x.p[0] = p; x.p[1] = x.p[2] = nullptr; x.block_rows = rows > 0 ? rows : 1; x.block_stride = 0; x.nptr = 1; x.d = d;
+  return x;
+}
 struct NoStoreEpi {
   float* C; int64_t ldc;
   struct Const { int col; };
@@ -94,7 +99,7 @@ int main() {
     struct T { const char* name; int N; int64_t lda; int64_t ldc; } ts[] = {
         {"fwd ZGR  [M,128]x[128,384] lda=128 ldc=512", 384, 128, 512}, {"fwd H    [M,128]x[128,128] lda=128 ldc=512", 128, 128, 512},
         {"fwd ZGR  [M,128]x[128,384] lda=128 ldc=384", 384, 128, 384}, {"fwd H    [M,128]x[128,128] lda=128 ldc=128", 128, 128, 128}};
-    for (int dbg : {0, 1, 4})
+    for (int dbg : {0})
     for (auto t : ts) {
       
       { int d = dbg & 3; CK(cudaMemcpyToSymbol(lg::g_lg_dbg, &d, 4)); }
@@ -117,6 +122,39 @@ int main() {
                (int)n, h[0] / n, h[1] / n, h[8] / n, h[9] / n, h[10] / n, h[16] / n, h[17] / n, h[18] / n, h[24] / n, h[25] / n, h[26] / n); }
     }
     CK(cudaGetLastError());
+    // ---- the fused DGM stages at the heat shapes (synthetic buffers) ----
+    {
+      int d0 = 0; CK(cudaMemcpyToSymbol(lg::g_lg_dbg, &d0, 4));
+      float *X, *UB, *S2, *SR, *SN;
+      CK(cudaMalloc(&X, M * 2 * 4)); CK(cudaMalloc(&UB, 512 * 16)); CK(cudaMalloc(&S2, M * 128 * 4)); CK(cudaMalloc(&SR, M * 128 * 4)); CK(cudaMalloc(&SN, M * 128 * 4));
+      CK(cudaMemset(X, 0, M * 2 * 4)); CK(cudaMemset(UB, 0, 512 * 16)); CK(cudaMemset(S2, 0, M * 128 * 4)); CK(cudaMemset(SR, 0, M * 128 * 4));
+      auto prof = [&](const char* name, float ms, double bytes) {
+        long long h[32]; CK(cudaMemcpyFromSymbol(h, lg::g_lg_prof, sizeof(h))); double n = (double)h[2];
+        printf("%s: %.3f ms  %.0f GB/s\n      cycles/tile (CTA 0, %d tiles): copy[wait_raw_empty %.0f total %.0f]  mma[wait_tcempty %.0f wait_opfull %.0f issue %.0f]  transform[wait_rawfull %.0f wait_opempty %.0f work %.0f]  epi[wait_tcfull %.0f drain %.0f epi %.0f]\n",
+               name, ms, bytes / ms * 1e-6, (int)n, h[0] / n, h[1] / n, h[8] / n, h[9] / n, h[10] / n, h[16] / n, h[17] / n, h[18] / n, h[24] / n, h[25] / n, h[26] / n);
+      };
+      {
+        using E1 = lg::DgmFwd1Epi<CsHeat, ACT_TANH>;
+        CK(cudaFuncSetAttribute(lg::lane_gemm_kernel<E1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lg::SMEM_BYTES));
+        E1 e; e.xs = xsrc1(X, M / 4, 2); e.A4 = C; e.ub = (const F4*)UB; e.S = S2; e.SR = SR;
+        float ms = time_ms([&] { lg::lane_gemm_kernel<<<147, lg::NT, lg::SMEM_BYTES>>>(S2, 128, B, K, (int64_t)512 * 512, M, 3, e); }, 10);
+        prof("fused Fwd1 heat (Z|G|R + act + s*R)", ms, (double)M * 512 * 5);
+      }
+      {
+        using E1 = lg::DgmFwd1Epi<CsV, ACT_TANH>;
+        CK(cudaFuncSetAttribute(lg::lane_gemm_kernel<E1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lg::SMEM_BYTES));
+        E1 e; e.xs = xsrc1(X, M, 2); e.A4 = C; e.ub = (const F4*)UB; e.S = S2; e.SR = SR;
+        float ms = time_ms([&] { lg::lane_gemm_kernel<<<147, lg::NT, lg::SMEM_BYTES>>>(S2, 128, B, K, (int64_t)512 * 512, M, 3, e); }, 10);
+        prof("fused Fwd1 value rows", ms, (double)M * 512 * 5);
+      }
+      {
+        using E2 = lg::DgmFwd2Epi<CsHeat, ACT_TANH>;
+        CK(cudaFuncSetAttribute(lg::lane_gemm_kernel<E2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lg::SMEM_BYTES));
+        E2 e; e.xs = xsrc1(X, M / 4, 2); e.A4 = C; e.ub = (const F4*)UB; e.S = S2; e.Sn = SN;
+        float ms = time_ms([&] { lg::lane_gemm_kernel<<<148, lg::NT, lg::SMEM_BYTES>>>(SR, 128, B, K, (int64_t)512 * 512, M, 1, e); }, 10);
+        prof("fused Fwd2 heat (H + act + state update)", ms, (double)M * 512 * 6);
+      }
+    }
   }
   printf("done\n");
   return 0;
