@@ -171,6 +171,13 @@ struct CudaBackend {
   // accumulation; everything else runs on the FP32 FFMA2 tile.
   void gemm_nn(const float* A, int64_t lda, const float* B, int64_t ldb, const float* Bt, int64_t ldbt, float* C,
                int64_t ldc, int64_t M, int N, int K, bool acc) {
+    // gridDim.y carries the row tiles (<= 65535): very tall operands go in slabs
+    constexpr int64_t SLAB = 65535LL * 128;
+    for (int64_t m0 = 0; m0 < M; m0 += SLAB)
+      gemm_nn_slab(A + m0 * lda, lda, B, ldb, Bt, ldbt, C + m0 * ldc, ldc, (M - m0 < SLAB) ? M - m0 : SLAB, N, K, acc);
+  }
+  void gemm_nn_slab(const float* A, int64_t lda, const float* B, int64_t ldb, const float* Bt, int64_t ldbt, float* C,
+                    int64_t ldc, int64_t M, int N, int K, bool acc) {
     if (M <= 0) return;
     if (use_tc && N % tc::BN == 0 && K % tc::KC == 0) {
       static bool attr_done = false;
@@ -211,10 +218,20 @@ struct CudaBackend {
       done_mask |= 1ull << (dev & 63);
     }
     const int64_t ntiles = (M + lg::NR - 1) / lg::NR;
-    int64_t grid = ntiles * ngates < sms ? ntiles * ngates : sms;
-    grid = grid / ngates * ngates;
-    if (grid < ngates) grid = ngates;
-    lg::lane_gemm_kernel<EPI><<<(unsigned)grid, lg::NT, lg::SMEM_BYTES, st>>>(X, ldx, Wt, ldw, hl_stride, M, ngates, epi);
+    int64_t grid, c0 = 0, c1 = 0;
+    if (ngates == 1) {
+      grid = ntiles < sms ? ntiles : sms;
+    } else {   // three gates; the third (R: also forms s*R) costs ~15 % more per tile
+      c0 = (int64_t)(sms / 3.15);
+      if (c0 > ntiles) c0 = ntiles;
+      if (c0 < 1) c0 = 1;
+      c1 = c0;
+      int64_t c2 = sms - 2 * c0;
+      if (c2 > ntiles) c2 = ntiles;
+      if (c2 < 1) c2 = 1;
+      grid = c0 + c1 + c2;
+    }
+    lg::lane_gemm_kernel<EPI><<<(unsigned)grid, lg::NT, lg::SMEM_BYTES, st>>>(X, ldx, Wt, ldw, hl_stride, M, ngates, (int)c0, (int)c1, epi);
     post();
   }
   // one DGM layer forward: [Z|G|R] GEMM + gate activations + s*R, then the H GEMM + activation +

@@ -46,12 +46,13 @@ namespace lg {
 
 #ifdef DGMK_LG_DEBUG   // microbenchmark-only switches: bit 0 = skip the MMAs, bit 1 = skip the transform stores
 __device__ int g_lg_dbg = 0;
+__device__ int g_lg_prof_cta = 0;
 __device__ long long g_lg_prof[32];
 #define LG_DBG(bit) (g_lg_dbg & (bit))
 #define LG_T(var) long long var = clock64()
 #define LG_ADD(slot, t0) lg_prof[slot] += clock64() - (t0)
 #define LG_PROF_DECL long long lg_prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}
-#define LG_PROF_OUT(base) if (blockIdx.x == 0 && lane == 0) { for (int q_ = 0; q_ < 8; ++q_) g_lg_prof[(base) + q_] = lg_prof[q_]; }
+#define LG_PROF_OUT(base) if (blockIdx.x == g_lg_prof_cta && lane == 0) { for (int q_ = 0; q_ < 8; ++q_) g_lg_prof[(base) + q_] = lg_prof[q_]; }
 #else
 #define LG_DBG(bit) 0
 #define LG_T(var)
@@ -176,12 +177,15 @@ struct StoreEpi {
   }
 };
 
-// grid = any multiple of ngates (<= #SMs).  X: [M, 128] rows with leading dimension ldx; Wt:
-// [ngates*128, 128] K-major with its tf32 hi / lo copies hl_stride / 2*hl_stride further.
+// X: [M, 128] rows with leading dimension ldx; Wt: [ngates*128, 128] K-major with its tf32 hi / lo
+// copies hl_stride / 2*hl_stride further.  CTAs [0, c0) work on gate 0, [c0, c0+c1) on gate 1, the
+// rest on gate 2 (ngates == 3) -- the gates need not get the same number of CTAs: the R gate of a
+// DGM layer also forms s*R and costs ~15 % more per tile (measured), so it gets more of them and
+// all three sweep the rows at the same pace (which also keeps the shared row tiles in L2).
 template <class EPI>
 __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restrict__ X, int64_t ldx,
                                                           const float* __restrict__ Wt, int64_t ldw, int64_t hl_stride,
-                                                          int64_t M, int ngates, const EPI epi) {
+                                                          int64_t M, int ngates, int c0, int c1, const EPI epi) {
   extern __shared__ __align__(128) char smem[];
   const uint32_t bar0 = tc::smem_u32(smem + BAR_OFF);
   const uint32_t RAW_FULL = bar0, RAW_EMPTY = bar0 + 24, OP_FULL = bar0 + 48, OP_EMPTY = bar0 + 64, TC_FULL = bar0 + 80,
@@ -189,8 +193,10 @@ __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restric
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 144);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int gate = blockIdx.x % ngates;
-  const int64_t grp = blockIdx.x / ngates, ngrp = gridDim.x / ngates;
+  const int b = blockIdx.x;
+  const int gate = (ngates == 1 || b < c0) ? 0 : (b < c0 + c1 ? 1 : 2);
+  const int64_t grp = (gate == 0) ? b : (gate == 1 ? b - c0 : b - c0 - c1);
+  const int64_t ngrp = (ngates == 1) ? gridDim.x : (gate == 0 ? c0 : (gate == 1 ? c1 : (int)gridDim.x - c0 - c1));
   const int64_t ntiles = (M + NR - 1) / NR;
 
   if (warp == 1) {
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restric
   // The epilogue warps hold the prefetch ring and the accumulators: setmaxnreg (one per warpgroup,
   // at the top of its role branch so that ptxas allocates each branch against its own limit) gives
   // them the registers the copy / MMA / transform warps do not need.
-  if (blockIdx.x < ngrp * ngates) {
+  {
    if (warp < W_TRANSFORM) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS_PRODUCER));
     if (warp == 0) {

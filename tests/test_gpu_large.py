@@ -95,3 +95,25 @@ def test_zero_residual_known_answer():
     expect = (J[:, 0, 1] ** 2).mean() + ((y0[:, 0] - torch.sin(a[1][:, 0])) ** 2).mean() \
         + (yb1 ** 2).mean() + (yb2 ** 2).mean()
     assert abs(out[-1].item() - expect.item()) <= 1e-5 * abs(expect.item())
+
+
+def test_fredholm_k1024_tall_operands():
+    """BASELINE configs[3]: 2^14 points x 1024 quadrature nodes = 16.8 M value rows in one chunk --
+    taller than one gridDim.y worth of row tiles (the GEMM front end goes in slabs).  Property:
+    the step of the whole batch equals the sum of the steps of two unequal shards (same B_global)."""
+    from differential_equations_dnn_b200 import kernels as K, _cabi
+    torch.manual_seed(0)
+    d = _cabi.make_desc(_cabi.KIND_DGM_RAW, 1, 1, 32, 1, _cabi.ACT_RELU)
+    theta = ((torch.rand(K.param_count(d)) - 0.5) * 0.4).cuda()
+    B, k = 1 << 14, 1024
+    gen = torch.Generator().manual_seed(4)
+    x = ((torch.pi / 2) * torch.rand(B, 1, generator=gen)).cuda()
+    T = ((torch.pi / 2) * torch.rand(k, B, 1, generator=gen)).cuda()
+    whole = K.fredholm_step(d, theta, x, T).double().cpu().numpy()
+    assert np.all(np.isfinite(whole))
+    cut = 5000
+    parts = 0.0
+    for lo, hi in ((0, cut), (cut, B)):
+        parts = parts + K.fredholm_step(d, theta, x[lo:hi].contiguous(), T[:, lo:hi].contiguous(), B_global=B).double().cpu().numpy()
+    assert abs(parts[-1] - whole[-1]) <= 1e-5 * abs(whole[-1])
+    assert np.linalg.norm(parts[:-1] - whole[:-1]) <= 1e-5 * np.linalg.norm(whole[:-1])

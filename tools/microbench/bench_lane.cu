@@ -80,8 +80,8 @@ int main() {
     naive_nt<<<(unsigned)((c.M * c.N + 255) / 256), 256>>>(A, lda, B, ldb, Cr, ldc, c.M, c.N, K, c.accum);
     int ng = c.N / 128;
     int grid = c.grid / ng * ng; if (grid < ng) grid = ng;
-    if (c.accum) { lg::StoreEpi<true> e{C, ldc}; lg::lane_gemm_kernel<<<grid, lg::NT, lg::SMEM_BYTES>>>(A, lda, B, ldb, (int64_t)c.N * ldb, c.M, ng, e); }
-    else { lg::StoreEpi<false> e{C, ldc}; lg::lane_gemm_kernel<<<grid, lg::NT, lg::SMEM_BYTES>>>(A, lda, B, ldb, (int64_t)c.N * ldb, c.M, ng, e); }
+    if (c.accum) { lg::StoreEpi<true> e{C, ldc}; lg::lane_gemm_kernel<<<grid, lg::NT, lg::SMEM_BYTES>>>(A, lda, B, ldb, (int64_t)c.N * ldb, c.M, ng, grid / 3, grid / 3, e); }
+    else { lg::StoreEpi<false> e{C, ldc}; lg::lane_gemm_kernel<<<grid, lg::NT, lg::SMEM_BYTES>>>(A, lda, B, ldb, (int64_t)c.N * ldb, c.M, ng, grid / 3, grid / 3, e); }
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     std::vector<float> r1(hC.size()), r2(hC.size());
@@ -111,9 +111,9 @@ int main() {
       int ng = t.N / 128, g = 148 / ng * ng;
       lg::StoreEpi<false> e{C, t.ldc};
       NoStoreEpi e2{C, 512};
-      if (nostore) ms = time_ms([&] { lg::lane_gemm_kernel<<<g, lg::NT, lg::SMEM_BYTES>>>(A, t.lda, B, K, (int64_t)512 * 512, M, ng, e2); }, 10);
+      if (nostore) ms = time_ms([&] { lg::lane_gemm_kernel<<<g, lg::NT, lg::SMEM_BYTES>>>(A, t.lda, B, K, (int64_t)512 * 512, M, ng, g / 3, g / 3, e2); }, 10);
       else
-      ms = time_ms([&] { lg::lane_gemm_kernel<<<g, lg::NT, lg::SMEM_BYTES>>>(A, t.lda, B, K, (int64_t)512 * 512, M, ng, e); }, 10);
+      ms = time_ms([&] { lg::lane_gemm_kernel<<<g, lg::NT, lg::SMEM_BYTES>>>(A, t.lda, B, K, (int64_t)512 * 512, M, ng, g / 3, g / 3, e); }, 10);
       double bytes = (double)M * (128 + t.N) * 4;
       printf("   lane_gemm %.3f ms  %.2f TFLOP/s  %.0f GB/s (algorithmic)\n", ms, 2.0 * M * t.N * K / ms * 1e-9, bytes / ms * 1e-6);
       { long long h[32]; CK(cudaMemcpyFromSymbol(h, lg::g_lg_prof, sizeof(h)));
@@ -128,6 +128,7 @@ int main() {
       float *X, *UB, *S2, *SR, *SN;
       CK(cudaMalloc(&X, M * 2 * 4)); CK(cudaMalloc(&UB, 512 * 16)); CK(cudaMalloc(&S2, M * 128 * 4)); CK(cudaMalloc(&SR, M * 128 * 4)); CK(cudaMalloc(&SN, M * 128 * 4));
       CK(cudaMemset(X, 0, M * 2 * 4)); CK(cudaMemset(UB, 0, 512 * 16)); CK(cudaMemset(S2, 0, M * 128 * 4)); CK(cudaMemset(SR, 0, M * 128 * 4));
+      const int c0g = 47;   // 47 | 47 | 54 CTAs for Z | G | R
       auto prof = [&](const char* name, float ms, double bytes) {
         long long h[32]; CK(cudaMemcpyFromSymbol(h, lg::g_lg_prof, sizeof(h))); double n = (double)h[2];
         printf("%s: %.3f ms  %.0f GB/s\n      cycles/tile (CTA 0, %d tiles): copy[wait_raw_empty %.0f total %.0f]  mma[wait_tcempty %.0f wait_opfull %.0f issue %.0f]  transform[wait_rawfull %.0f wait_opempty %.0f work %.0f]  epi[wait_tcfull %.0f drain %.0f epi %.0f]\n",
@@ -137,21 +138,27 @@ int main() {
         using E1 = lg::DgmFwd1Epi<CsHeat, ACT_TANH>;
         CK(cudaFuncSetAttribute(lg::lane_gemm_kernel<E1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lg::SMEM_BYTES));
         E1 e; e.xs = xsrc1(X, M / 4, 2); e.A4 = C; e.ub = (const F4*)UB; e.S = S2; e.SR = SR;
-        float ms = time_ms([&] { lg::lane_gemm_kernel<<<147, lg::NT, lg::SMEM_BYTES>>>(S2, 128, B, K, (int64_t)512 * 512, M, 3, e); }, 10);
+        float ms = time_ms([&] { lg::lane_gemm_kernel<<<148, lg::NT, lg::SMEM_BYTES>>>(S2, 128, B, K, (int64_t)512 * 512, M, 3, c0g, c0g, e); }, 10);
         prof("fused Fwd1 heat (Z|G|R + act + s*R)", ms, (double)M * 512 * 5);
+        int c2 = 100; CK(cudaMemcpyToSymbol(lg::g_lg_prof_cta, &c2, 4));
+        ms = time_ms([&] { lg::lane_gemm_kernel<<<148, lg::NT, lg::SMEM_BYTES>>>(S2, 128, B, K, (int64_t)512 * 512, M, 3, c0g, c0g, e); }, 10);
+        prof("   same, counters of CTA 2 (R gate)", ms, (double)M * 512 * 5);
       }
       {
         using E1 = lg::DgmFwd1Epi<CsV, ACT_TANH>;
         CK(cudaFuncSetAttribute(lg::lane_gemm_kernel<E1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lg::SMEM_BYTES));
         E1 e; e.xs = xsrc1(X, M, 2); e.A4 = C; e.ub = (const F4*)UB; e.S = S2; e.SR = SR;
-        float ms = time_ms([&] { lg::lane_gemm_kernel<<<147, lg::NT, lg::SMEM_BYTES>>>(S2, 128, B, K, (int64_t)512 * 512, M, 3, e); }, 10);
-        prof("fused Fwd1 value rows", ms, (double)M * 512 * 5);
+        float ms = time_ms([&] { lg::lane_gemm_kernel<<<148, lg::NT, lg::SMEM_BYTES>>>(S2, 128, B, K, (int64_t)512 * 512, M, 3, c0g, c0g, e); }, 10);
+        prof("   value rows, CTA 2 (R gate)", ms, (double)M * 512 * 5);
+        int c0 = 0; CK(cudaMemcpyToSymbol(lg::g_lg_prof_cta, &c0, 4));
+        ms = time_ms([&] { lg::lane_gemm_kernel<<<148, lg::NT, lg::SMEM_BYTES>>>(S2, 128, B, K, (int64_t)512 * 512, M, 3, c0g, c0g, e); }, 10);
+        prof("fused Fwd1 value rows (CTA 0, Z gate)", ms, (double)M * 512 * 5);
       }
       {
         using E2 = lg::DgmFwd2Epi<CsHeat, ACT_TANH>;
         CK(cudaFuncSetAttribute(lg::lane_gemm_kernel<E2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lg::SMEM_BYTES));
         E2 e; e.xs = xsrc1(X, M / 4, 2); e.A4 = C; e.ub = (const F4*)UB; e.S = S2; e.Sn = SN;
-        float ms = time_ms([&] { lg::lane_gemm_kernel<<<148, lg::NT, lg::SMEM_BYTES>>>(SR, 128, B, K, (int64_t)512 * 512, M, 1, e); }, 10);
+        float ms = time_ms([&] { lg::lane_gemm_kernel<<<148, lg::NT, lg::SMEM_BYTES>>>(SR, 128, B, K, (int64_t)512 * 512, M, 1, 0, 0, e); }, 10);
         prof("fused Fwd2 heat (H + act + state update)", ms, (double)M * 512 * 6);
       }
     }
