@@ -226,10 +226,24 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t[0].item(), t[1].item(), clocks, launches, out
 
+    lib.dgmk_profile(1)   # CUDA events around every kernel class of the library, on the launch stream
     ms, wall_ms, clocks, launches, last = timed(step_resident, W, a.steps, True)
+    lib.dgmk_profile(0)
     ms_step = ms / a.steps
     rows = B * max(world, 1)
     value = rows / (ms_step * 1e-3)
+    prof = {}
+    names = {0: "wg::wgrad_ws_kernel (weight gradient: warp-specialised tcgen05 kind::tf32, A^T in tensor memory, 3xTF32)",
+             1: "lg::lane_gemm_kernel (fused GEMM + jet stage: weights in tensor memory, warp-specialised, 3xTF32)",
+             2: "tc::gemm_nn_tc_kernel (streaming tcgen05 tile: K = 3H data gradient; FFMA2 tile for H % 128 != 0)",
+             3: "ew_kernel<...> (stand-alone element-wise jet stages, loss, pack, Adam)"}
+    for cls in range(4):
+        t_, n_, f_, b_ = C.c_double(), C.c_longlong(), C.c_double(), C.c_double()
+        _cabi.check(lib.dgmk_profile_read(cls, C.byref(t_), C.byref(n_), C.byref(f_), C.byref(b_)))
+        per_step = (W + a.steps)   # the profile spans warm-up + timed steps: identical work per step
+        if n_.value:
+            prof[cls] = {"kernel": names[cls], "ms_per_step": t_.value / per_step, "launches_per_step": n_.value / per_step,
+                         "alg_flops_per_step": f_.value / per_step, "alg_bytes_per_step": b_.value / per_step}
     e_ms, e_wall, _, _, _ = timed(step_e2e, 2, a.steps, False)
     e_step = max(e_ms, e_wall) / a.steps      # host-side copies/sync: take the larger clock
     e2e_value = rows / (e_step * 1e-3)
@@ -239,15 +253,16 @@ def main():
             dist.barrier()
             dist.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel, measured live --------------------------------------
-    # Dominant kernel (profiles/: ~1/3 of the step): tc::gemm_nn_tc_kernel, the tcgen05 kind::tf32
-    # tile with 3xTF32 split accumulation, at the step's forward Z|G|R shape.  `achieved` counts
-    # ALGORITHMIC flops (2*M*N*K); the kernel issues 3 TF32 MMAs per algorithmic product to keep
-    # FP32-grade accuracy, so its own ceiling is peak/3.
+    # ---- roofline of the dominant kernel, from the timed region itself ------------------------
+    # The library brackets every launch of a kernel class with CUDA events on its stream
+    # (dgmk_profile) and sums the launch's ALGORITHMIC flops (2*M*N*K) and bytes (each operand /
+    # result once).  The dominant class is the one with the largest summed duration.  Its tensor
+    # roofline: peak = dense TF32 = 1/2 of the measured bf16 figure (sustained: timed inside a long
+    # step); the kernels issue 3 TF32 MMAs per algorithmic product (FP32-grade accuracy), so their
+    # own ceiling is peak/3 -- reported as frac_of_3xtf32_ceiling next to the HBM fraction.
     fl_row = f_alg(H, L)
     roof = None
     try:
-        Hp = (H + 31) // 32 * 32
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -272,43 +287,53 @@ def main():
         mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(mp):
             peaks = json.load(open(mp))
-        bf16 = peaks.get("bf16_tflops", 1590.0)
-        bf16_src = "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback 1590 (B200_PROFILING.md)"
-        tc_ok = Hp % 128 == 0
-        Mrows = 4 * min(B, 1 << 17)
-        A_ = torch.randn(Mrows, 4 * Hp, device=dev)
-        C_ = torch.empty(Mrows, 4 * Hp, device=dev)
-        if tc_ok:
-            Bt_ = torch.randn(3, 3 * Hp, Hp, device=dev)      # plain | tf32-hi | tf32-lo copies
-            k_ms = timeit(lambda: _cabi.check(lib.dgmk_gemm_tc_probe(
-                C.c_void_p(A_.data_ptr()), C.c_void_p(Bt_.data_ptr()), C.c_void_p(C_.data_ptr()),
-                Mrows, 3 * Hp, Hp, 4 * Hp, st)), 10)
-            achieved = 2.0 * Mrows * 3 * Hp * Hp / (k_ms * 1e-3) / 1e12
-            tf32_peak = bf16 / 2.0
-            roof = {"bound": "tensor",
-                    "kernel": "tc::gemm_nn_tc_kernel (tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators), "
-                              "fwd Z|G|R tile [M=%d,%d]x[%d,%d]" % (Mrows, Hp, Hp, 3 * Hp),
-                    "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
-                    "traffic": None,
-                    "peak_source": f"TF32 dense = 1/2 x {bf16_src} = {tf32_peak:.1f}; achieved counts algorithmic "
-                                   "2MNK flops, the kernel issues 3 TF32 MMAs per product",
-                    "tensor_issue_tflops": 3 * achieved, "frac_of_3xtf32_ceiling": 3 * achieved / tf32_peak}
+        bf16 = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
+        bf16_src = ("MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else
+                    "MEASURED_PEAKS.json bf16_tflops" if "bf16_tflops" in peaks else "fallback 1590 (B200_PROFILING.md)")
+        hbm = peaks.get("hbm_gbs", 6500.0)
+        tf32_peak = bf16 / 2.0
+        kernels_ = {}
+        for cls, p in prof.items():
+            t = p["ms_per_step"] * 1e-3
+            kernels_[str(cls)] = dict(p, share_of_step=p["ms_per_step"] / ms_step,
+                                      achieved_tflops=p["alg_flops_per_step"] / t / 1e12 if p["alg_flops_per_step"] else None,
+                                      achieved_gbs=p["alg_bytes_per_step"] / t / 1e9 if p["alg_bytes_per_step"] else None)
+        gemm_cls = [c for c in prof if prof[c]["alg_flops_per_step"]]
+        dom = max(gemm_cls, key=lambda c: prof[c]["ms_per_step"])
+        k = kernels_[str(dom)]
+        per_launch = 1.0 / k["launches_per_step"]
+        tensor_frac3 = 3 * k["achieved_tflops"] / tf32_peak      # against the kernel's own 3xTF32 ceiling
+        hbm_frac = k["achieved_gbs"] / hbm
+        common = {"kernel": k["kernel"], "traffic": None,
+                  "launch": {"avg_ms": k["ms_per_step"] * per_launch, "alg_flops": k["alg_flops_per_step"] * per_launch,
+                             "alg_bytes": k["alg_bytes_per_step"] * per_launch, "per_step": k["launches_per_step"]},
+                  "tensor_tflops_algorithmic": k["achieved_tflops"], "tensor_issue_tflops": 3 * k["achieved_tflops"],
+                  "tf32_peak_tflops": tf32_peak, "frac_of_tf32_peak": k["achieved_tflops"] / tf32_peak,
+                  "frac_of_3xtf32_ceiling": tensor_frac3,
+                  "hbm_gbs": k["achieved_gbs"], "hbm_peak_gbs": hbm, "hbm_frac": hbm_frac,
+                  "share_of_step": k["share_of_step"], "kernel_classes": kernels_}
+        if hbm_frac >= tensor_frac3:   # the bound the kernel is closer to
+            roof = dict(common, bound="hbm", achieved=k["achieved_gbs"], peak=hbm, unit="GB/s", frac=hbm_frac,
+                        peak_source="MEASURED_PEAKS.json hbm_gbs; achieved = ALGORITHMIC bytes of the class's launches (every "
+                                    "operand / result once: DESIGN.md section 3) / their CUDA-event durations inside the timed steps")
         else:
-            B_ = torch.randn(Hp, 3 * Hp, device=dev)
-            k_ms = timeit(lambda: _cabi.check(lib.dgmk_gemm_probe(
-                C.c_void_p(A_.data_ptr()), C.c_void_p(B_.data_ptr()), C.c_void_p(C_.data_ptr()),
-                Mrows, 3 * Hp, Hp, 4 * Hp, st)), 10)
-            achieved = 2.0 * Mrows * 3 * Hp * Hp / (k_ms * 1e-3) / 1e12
-            roof = {"bound": "fp32", "kernel": "gemm_nn_kernel<FFMA2> fwd tile", "achieved": achieved,
-                    "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
-                    "peak_source": "FP32 FFMA chain probe measured live (dgmk_ffma_probe)"}
+            roof = dict(common, bound="tensor", achieved=k["achieved_tflops"], peak=tf32_peak, unit="TFLOP/s",
+                        frac=k["achieved_tflops"] / tf32_peak,
+                        peak_source=f"TF32 dense = 1/2 x {bf16_src} = {tf32_peak:.1f} TFLOP/s; achieved = algorithmic 2MNK "
+                                    "flops of the class's launches / their CUDA-event durations inside the timed steps "
+                                    "(the kernel issues 3 TF32 MMAs per product: its own ceiling is peak/3)")
         # the north star's framing: whole step against the FP32 FFMA roofline of the reference path
         roof.update({"fp32_ffma_peak_live": fp32_peak, "alg_flops_per_row": fl_row,
                      "step_achieved": fl_row * B / (ms_step * 1e-3) / 1e12,
                      "step_frac_of_fp32_peak": fl_row * B / (ms_step * 1e-3) / 1e12 / fp32_peak})
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr):
-            roof["traffic"] = json.load(open(tr)).get("gemm_nn_tc_bytes_per_launch")
+            tj = json.load(open(tr))
+            key = {0: "wgrad_ws", 1: "lane_gemm", 2: "gemm_nn_tc"}.get(dom)
+            ratio = tj.get(key + "_dram_over_algorithmic")
+            if ratio is not None:   # ncu dram__bytes_read+write per launch / algorithmic bytes of that launch
+                roof["traffic"] = ratio * roof["launch"]["alg_bytes"]
+                roof["traffic_source"] = tj.get(key + "_source")
     except Exception as e:  # the number above is still valid without the probe
         roof = {"error": repr(e)}
 

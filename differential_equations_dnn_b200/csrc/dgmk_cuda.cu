@@ -3,6 +3,7 @@
 //        --expt-relaxed-constexpr -Xcompiler -fPIC -shared -o libdgmk.so dgmk_cuda.cu
 // This is the only implementation the package loads: there is no CPU path.
 #include <cuda_runtime.h>
+#include <vector>
 #include "dgmk_capi_impl.h"
 #include "dgmk_gemm.cuh"
 #include "dgmk_gemm_tc.cuh"
@@ -22,6 +23,41 @@ static unsigned long long g_launches = 0;
 static bool g_use_tc = true;
 // fused units-on-lanes kernels (GEMM + element-wise stage in one launch) where the shape allows
 static bool g_fuse = true;
+
+// ---- per-kernel-class timing (dgmk_profile*): CUDA events recorded on the launch stream around
+// every launch of a class, with the launch's ALGORITHMIC flops and bytes, so that bench.py can
+// report the roofline of the dominant kernel from the timed region itself ----------------------
+enum { PC_WGRAD = 0, PC_LANE = 1, PC_STREAM_NN = 2, PC_EW = 3, PC_OTHER = 4, PC_COUNT = 5 };
+struct ProfClass {
+  std::vector<cudaEvent_t> ev;   // begin, end, begin, end, ...
+  double flops = 0.0, bytes = 0.0;
+  long long launches = 0;
+};
+static bool g_prof_on = false;
+static ProfClass g_prof[PC_COUNT];
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+struct ProfScope {   // records begin now, end at destruction
+  int cls; cudaStream_t st; bool on;
+  ProfScope(int c, cudaStream_t s, double flops, double bytes) : cls(c), st(s), on(g_prof_on) {
+    if (!on) return;
+    cudaEvent_t e = prof_event();
+    cudaEventRecord(e, st);
+    g_prof[cls].ev.push_back(e);
+    g_prof[cls].flops += flops; g_prof[cls].bytes += bytes; g_prof[cls].launches += 1;
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEvent_t e = prof_event();
+    cudaEventRecord(e, st);
+    g_prof[cls].ev.push_back(e);
+  }
+};
 
 template <class F>
 __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const F f, int64_t n) {
@@ -163,6 +199,7 @@ struct CudaBackend {
     int64_t blocks = (n + EW_THREADS - 1) / EW_THREADS;
     int64_t cap = (int64_t)sms * 32;
     if (blocks > cap) blocks = cap;
+    ProfScope ps(PC_EW, st, 0.0, 0.0);
     ew_kernel<F><<<(unsigned)blocks, EW_THREADS, 0, st>>>(f, n);
     post();
   }
@@ -179,6 +216,7 @@ struct CudaBackend {
   void gemm_nn_slab(const float* A, int64_t lda, const float* B, int64_t ldb, const float* Bt, int64_t ldbt, float* C,
                     int64_t ldc, int64_t M, int N, int K, bool acc) {
     if (M <= 0) return;
+    ProfScope ps(PC_STREAM_NN, st, 2.0 * M * N * K, 4.0 * M * (K + (acc ? 2.0 : 1.0) * N));
     if (use_tc && N % tc::BN == 0 && K % tc::KC == 0) {
       static bool attr_done = false;
       if (!attr_done) {
@@ -206,9 +244,11 @@ struct CudaBackend {
   bool lane_ok(int Hp, int cs) const {
     return use_tc && fuse && Hp == lg::KTOT && (cs == CS_V || cs == CS_D1O1 || cs == CS_HEAT);
   }
+  // `units`: algorithmic HBM traffic of the launch in [M, 128] FP32 matrices (read + written)
   template <class EPI>
-  void lane_gemm(const float* X, int64_t ldx, const float* Wt, int64_t ldw, int64_t M, int ngates, const EPI& epi) {
+  void lane_gemm(const float* X, int64_t ldx, const float* Wt, int64_t ldw, int64_t M, int ngates, const EPI& epi, double units) {
     if (M <= 0) return;
+    ProfScope ps(PC_LANE, st, 2.0 * M * lg::NU * lg::KTOT * ngates, units * M * lg::KTOT * 4.0);
     // opt-in shared memory size: per function and per device
     static unsigned long long done_mask = 0;
     int dev = 0;
@@ -241,9 +281,9 @@ struct CudaBackend {
                      int64_t M) {
     if constexpr (CS::C == 1 || CS::C == 2 || CS::C == 4) {
       lg::DgmFwd1Epi<CS, ACT> e1; e1.xs = xs; e1.A4 = A4; e1.ub = ub; e1.S = S; e1.SR = SR;
-      lane_gemm(S, Hp, Wb, Hp, M, 3, e1);
+      lane_gemm(S, Hp, Wb, Hp, M, 3, e1, 5.0);       // read s; write Z, G, R a-forms, s*R
       lg::DgmFwd2Epi<CS, ACT> e2; e2.xs = xs; e2.A4 = A4; e2.ub = ub; e2.S = S; e2.Sn = Sn;
-      lane_gemm(SR, Hp, Wb + (int64_t)3 * Hp * Hp, Hp, M, 1, e2);
+      lane_gemm(SR, Hp, Wb + (int64_t)3 * Hp * Hp, Hp, M, 1, e2, 6.0);   // read s*R, Z, G, s; write H a-form, s'
     } else if (!err) err = "internal: fused path called with an unsupported channel set";
   }
   // (s*R)bar = abar_H W_h fused with the R-gate adjoint (DgmRev2Fn).  Wfh = packed [Hp in, Hp out]
@@ -251,7 +291,7 @@ struct CudaBackend {
   void dgm_rev2_fused(const float* A4, const float* S, float* AB4, float* SBp, const float* Wfh, int Hp, int64_t M) {
     if constexpr (CS::C == 1 || CS::C == 2 || CS::C == 4) {
       lg::DgmRev2Epi<CS, ACT> e; e.A4 = A4; e.S = S; e.AB4 = AB4; e.SBp = SBp;
-      lane_gemm(AB4 + 3 * Hp, 4 * (int64_t)Hp, Wfh, Hp, M, 1, e);
+      lane_gemm(AB4 + 3 * Hp, 4 * (int64_t)Hp, Wfh, Hp, M, 1, e, 6.0);   // read abar_H, R a-form, s, s bar; write abar_R, s bar
     } else if (!err) err = "internal: fused path called with an unsupported channel set";
   }
   // MLP hidden layer forward: GEMM + bias + activation
@@ -259,13 +299,13 @@ struct CudaBackend {
   void mlp_fwd_fused(const float* Yp, float* G, const F4* ub, float* Yn, const float* Wb, int Hp, int64_t M) {
     if constexpr (CS::C == 1 || CS::C == 2 || CS::C == 4) {
       lg::MlpActEpi<CS, ACT> e; e.G = G; e.ub = ub; e.Yn = Yn;
-      lane_gemm(Yp, Hp, Wb, Hp, M, 1, e);
+      lane_gemm(Yp, Hp, Wb, Hp, M, 1, e, 3.0);
     } else if (!err) err = "internal: fused path called with an unsupported channel set";
   }
   // C[M, Hp] = X[M, Hp] Wt[Hp, Hp]^T on the lane kernel (MLP data gradient)
   void lane_store(const float* X, int64_t ldx, const float* Wt, float* C, int64_t ldc, int Hp, int64_t M) {
     lg::StoreEpi<false> e; e.C = C; e.ldc = ldc;
-    lane_gemm(X, ldx, Wt, Hp, M, 1, e);
+    lane_gemm(X, ldx, Wt, Hp, M, 1, e, 2.0);
   }
   void reduce(const float* part, int nparts, int64_t n, float* out) {
     reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, nparts, n, out);
@@ -320,6 +360,7 @@ struct CudaBackend {
         note(cudaFuncSetAttribute(wg::wgrad_ws_kernel<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES));
         done_mask |= 1ull << (dev & 63);
       }
+      ProfScope ps(PC_WGRAD, st, 2.0 * M * N * Kd, 4.0 * M * (N + Kd + 4.0));
       if (lda == 512) wg::wgrad_ws_kernel<512, 128><<<gws, wg::NT, wg::SMEM_BYTES, st>>>(A, S, E, part, PEw, N, Kd, M, seg_rows, (int)nseg);
       else wg::wgrad_ws_kernel<128, 128><<<gws, wg::NT, wg::SMEM_BYTES, st>>>(A, S, E, part, PEw, N, Kd, M, seg_rows, (int)nseg);
       post();
@@ -413,6 +454,38 @@ __global__ void __launch_bounds__(256) ffma_probe_kernel(float* out, const float
 
 extern "C" {
 unsigned long long dgmk_launch_count(void) { return dgmk::g_launches; }
+// Per-kernel-class timing.  dgmk_profile(1) clears the counters and starts recording CUDA events
+// around every launch; dgmk_profile(0) stops.  dgmk_profile_read(cls, ...) synchronises the
+// recorded events and returns the class's summed duration [ms], launches, algorithmic flops and
+// bytes.  Classes: 0 weight gradient (wgrad_ws), 1 fused units-on-lanes GEMM + element-wise kernels,
+// 2 streaming tcgen05 / FFMA GEMM tiles, 3 stand-alone element-wise kernels.
+void dgmk_profile(int on) {
+  using namespace dgmk;
+  if (on) {
+    for (int c = 0; c < PC_COUNT; ++c) {
+      for (cudaEvent_t e : g_prof[c].ev) g_prof_pool.push_back(e);
+      g_prof[c] = ProfClass();
+    }
+  }
+  g_prof_on = on != 0;
+}
+int dgmk_profile_read(int cls, double* ms, long long* launches, double* flops, double* bytes) {
+  using namespace dgmk;
+  if (cls < 0 || cls >= PC_COUNT) return DGMK_EINVAL;
+  ProfClass& p = g_prof[cls];
+  double total = 0.0;
+  for (size_t i = 0; i + 1 < p.ev.size(); i += 2) {
+    if (cudaEventSynchronize(p.ev[i + 1]) != cudaSuccess) return DGMK_ECUDA;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, p.ev[i], p.ev[i + 1]) != cudaSuccess) return DGMK_ECUDA;
+    total += t;
+  }
+  if (ms) *ms = total;
+  if (launches) *launches = p.launches;
+  if (flops) *flops = p.flops;
+  if (bytes) *bytes = p.bytes;
+  return 0;
+}
 // 0 = FP32 FFMA2 tiles only; 1 = tcgen05 3xTF32, fused GEMM + element-wise kernels where the shape
 // allows (default); 2 = tcgen05 3xTF32 streaming tiles + separate element-wise kernels
 void dgmk_set_gemm_engine(int engine) { dgmk::g_use_tc = engine != 0; dgmk::g_fuse = engine == 1; }

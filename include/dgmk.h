@@ -130,7 +130,16 @@ int dgmk_adam(float* theta, float* m, float* v, const float* grad, const uint8_t
 /* ---- diagnostics used by bench.py (not reference-facing) --------------------------- */
 unsigned long long dgmk_launch_count(void); /* kernels launched by this library so far */
 int dgmk_ffma_probe(const float* in, float* out, int blocks, int iters, void* stream);
-void dgmk_set_gemm_engine(int tensor_cores); /* 0: FFMA2 tiles only; 1 (default): tcgen05 3xTF32 where shapes allow */
+/* 0: FP32 FFMA2 tiles only; 1 (default): tcgen05 3xTF32, fused GEMM + element-wise kernels and the
+ * warp-specialised weight gradient where the shape allows; 2: tcgen05 3xTF32 streaming tiles +
+ * separate element-wise kernels */
+void dgmk_set_gemm_engine(int engine);
+/* Per-kernel-class timing with CUDA events on the launch stream.  dgmk_profile(1) clears and
+ * starts, dgmk_profile(0) stops; dgmk_profile_read synchronises the recorded events and returns the
+ * class's summed duration [ms], launches, ALGORITHMIC flops and bytes.  Classes: 0 weight gradient,
+ * 1 fused units-on-lanes GEMM + element-wise kernels, 2 streaming GEMM tiles, 3 element-wise. */
+void dgmk_profile(int on);
+int dgmk_profile_read(int cls, double* ms, long long* launches, double* flops, double* bytes);
 /* Bt holds three [N,K] copies back to back: plain | tf32-hi | tf32-lo */
 int dgmk_gemm_tc_probe(const float* A, const float* Bt, float* C, int64_t M, int N, int K, int64_t ld,
                        void* stream);
