@@ -55,6 +55,8 @@ _SIGNATURES = {
     "dgmk_eval": (C.c_int, [C.POINTER(NetDesc), _P, _P, C.c_int64, _P, _P, C.c_size_t, _P]),
     "dgmk_adam": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
                             C.c_int64, _P]),
+    "dgmk_adam_dev": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
+                                _P, _P]),
 }
 # diagnostics exported only by the CUDA library (bench.py)
 _CUDA_ONLY = {

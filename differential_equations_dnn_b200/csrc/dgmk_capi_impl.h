@@ -352,6 +352,23 @@ struct Api {
     bk.ew(f, P);
     return finish(bk);
   }
+  // same update with the step counter (and the two bias-correction scalars) in device memory:
+  // nothing in the launch depends on host state, so a captured CUDA graph can replay it
+  static int adam_dev(float* theta, float* m, float* v, const float* g, const uint8_t* live, int64_t P, double lr,
+                      double b1, double b2, double eps, long long* state, void* stream) {
+    if (P <= 0 || !state) return fail(DGMK_EINVAL, "need P > 0 and a 16-byte device state");
+    BK bk(stream);
+    const void* ptrs[] = {theta, m, v, g, state};
+    if (int r = check_common(bk, ptrs, 5, 1, 1)) return r;
+    if (live && !bk.is_device_ptr(live)) return fail(DGMK_EDEVICE, "live mask must be device memory");
+    AdamPrepFn pf; pf.state = state; pf.lr = lr; pf.b1 = b1; pf.b2 = b2;
+    bk.ew(pf, 1);
+    AdamDevFn f; f.theta = theta; f.m = m; f.v = v; f.g = g; f.live = live; f.state = state;
+    f.w1 = (float)(1.0 - b1);
+    f.b2 = (float)b2; f.w2 = (float)(1.0 - b2); f.eps = (float)eps;
+    bk.ew(f, P);
+    return finish(bk);
+  }
 };
 
 inline int param_layout(const dgmk_net_desc* desc, int32_t index, int64_t* offset, int32_t* rows, int32_t* cols, int32_t* live) {
@@ -431,4 +448,7 @@ inline size_t workspace_bytes(const dgmk_net_desc* desc, int32_t cls, int64_t B,
   int dgmk_adam(float* th, float* m, float* v, const float* g, const uint8_t* live, int64_t P, double lr,          \
                 double b1, double b2, double eps, int64_t step, void* st) {                                        \
     return dgmk::Api<BK>::adam(th, m, v, g, live, P, lr, b1, b2, eps, step, st); }                                 \
+  int dgmk_adam_dev(float* th, float* m, float* v, const float* g, const uint8_t* live, int64_t P, double lr,      \
+                    double b1, double b2, double eps, long long* state, void* st) {                                \
+    return dgmk::Api<BK>::adam_dev(th, m, v, g, live, P, lr, b1, b2, eps, state, st); }                            \
   }

@@ -474,4 +474,34 @@ struct AdamFn {
   }
 };
 
+// Device-resident step counter variant (CUDA-graph capturable training loops): state = 16 bytes,
+// [int64 step | float lr/(1-b1^t) | float sqrt(1-b2^t)].  AdamPrepFn (one thread) advances the
+// counter and forms the two bias-correction scalars in doubles exactly like torch does on the host;
+// AdamDevFn is AdamFn with those two scalars read from the state.
+struct AdamPrepFn {
+  long long* state; double lr, b1, b2;
+  DGMK_HD void operator()(int64_t) const {
+    const long long t = state[0] + 1;
+    state[0] = t;
+    float* sc = reinterpret_cast<float*>(state + 1);
+    sc[0] = (float)(lr / (1.0 - pow(b1, (double)t)));
+    sc[1] = (float)sqrt(1.0 - pow(b2, (double)t));
+  }
+};
+struct AdamDevFn {
+  float* theta; float* m; float* v; const float* g; const uint8_t* live; const long long* state;
+  float w1, b2, w2, eps;
+  DGMK_HD void operator()(int64_t i) const {
+    if (live && !live[i]) return;
+    const float* sc = reinterpret_cast<const float*>(state + 1);
+    const float step_size = sc[0], bc2_sqrt = sc[1];
+    float gi = g[i];
+    float mi = m[i] + w1 * (gi - m[i]);
+    float vi = b2 * v[i] + (w2 * gi) * gi;
+    m[i] = mi; v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    theta[i] -= step_size * (mi / denom);
+  }
+};
+
 }  // namespace dgmk

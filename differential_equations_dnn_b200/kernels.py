@@ -197,3 +197,16 @@ def adam_step(theta, m, v, grad, live, lr, beta1, beta2, eps, step):
         rc = lib.dgmk_adam(_ptr(theta), _ptr(m), _ptr(v), _ptr(grad), _ptr(live), theta.numel(), float(lr),
                            float(beta1), float(beta2), float(eps), int(step), _stream(theta.device))
     _cabi.check(rc, lib)
+
+
+def adam_step_dev(theta, m, v, grad, live, lr, beta1, beta2, eps, state):
+    """Same update with the step counter in device memory (`state`: 2 x int64, zero-initialised):
+    no host-side state, so a captured CUDA graph can replay it."""
+    _dev_f32(theta, m, v, grad)
+    if not (state.is_cuda and state.dtype == torch.int64 and state.numel() >= 2):
+        raise DgmkError("adam_step_dev needs a CUDA int64 state tensor of 2 elements")
+    lib = _cabi.load()
+    with torch.cuda.device(theta.device):
+        rc = lib.dgmk_adam_dev(_ptr(theta), _ptr(m), _ptr(v), _ptr(grad), _ptr(live), theta.numel(), float(lr),
+                               float(beta1), float(beta2), float(eps), _ptr(state), _stream(theta.device))
+    _cabi.check(rc, lib)

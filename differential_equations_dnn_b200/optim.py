@@ -4,6 +4,9 @@ Same defaults and arithmetic as torch.optim.Adam (betas 0.9/0.999, eps 1e-8, no 
 decay, no amsgrad); one kernel over [theta, m, v, grad] instead of ~12 tiny launches
 per parameter tensor.  Parameters whose `.grad` is None are skipped, like
 torch does -- that is how neural_networks.DGM's dead `dgm1` stays untouched.
+
+`capturable=True` keeps the step counter in device memory (torch.optim.Adam's flag of the same
+name), so that `step()` can be captured in a CUDA graph (heat.minimize_loss_dgm(cuda_graph=True)).
 """
 from __future__ import annotations
 
@@ -13,9 +16,11 @@ from . import kernels
 
 
 class FusedAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, capturable=False):
         params = list(params)
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self.capturable = bool(capturable)
+        self._state = None
         owner = getattr(params[0], "_dgmk_flat", (None, 0))[0]
         self.net = owner() if owner is not None else None
         if self.net is None or len(params) != len(self.net.param_slices()):
@@ -59,6 +64,12 @@ class FusedAdam(torch.optim.Optimizer):
         if self._live is None or self._live[0] != key:
             self._live = (key, mask.to(theta.device))
         g = self.param_groups[0]
+        if self.capturable:
+            if self._state is None or self._state.device != theta.device:
+                self._state = torch.zeros(2, dtype=torch.int64, device=theta.device)
+            kernels.adam_step_dev(theta, self._m, self._v, flat, self._live[1], g["lr"], g["betas"][0], g["betas"][1],
+                                  g["eps"], self._state)
+            return loss
         self._t += 1
         kernels.adam_step(theta, self._m, self._v, flat, self._live[1], g["lr"], g["betas"][0], g["betas"][1],
                           g["eps"], self._t)

@@ -127,6 +127,12 @@ int dgmk_eval(const dgmk_net_desc* desc, const float* theta, const float* x, int
 int dgmk_adam(float* theta, float* m, float* v, const float* grad, const uint8_t* live, int64_t P,
               double lr, double beta1, double beta2, double eps, int64_t step, void* stream);
 
+/* Same update with the step counter in device memory, for training loops captured in a CUDA graph
+ * (nothing in the launch depends on host state).  state: 16 bytes of device memory, zero-initialised
+ * by the caller = [int64 step count | 2 floats of scratch]; each call increments the count first. */
+int dgmk_adam_dev(float* theta, float* m, float* v, const float* grad, const uint8_t* live, int64_t P,
+                  double lr, double beta1, double beta2, double eps, long long* state, void* stream);
+
 /* ---- diagnostics used by bench.py (not reference-facing) --------------------------- */
 unsigned long long dgmk_launch_count(void); /* kernels launched by this library so far */
 int dgmk_ffma_probe(const float* in, float* out, int blocks, int iters, void* stream);
