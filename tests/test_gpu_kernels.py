@@ -71,7 +71,9 @@ def test_step_matches_reference(K, prob, name):
 
 
 @pytest.mark.parametrize("prob,name", [("heat", "heat_dgm_h32l1"), ("fredholm", "fredholm_dgmraw_h32l1_k7"),
-                                       ("fhn", "fhn_dgm_h64l2"), ("ode", "ode_mlp_relu_h32l1")])
+                                       ("fhn", "fhn_dgm_h64l2"), ("ode", "ode_mlp_relu_h32l1"),
+                                       # hidden size 128: the fused tcgen05 kernels on 5-row chunks (tiles mostly padding)
+                                       ("heat", "heat_dgm_h128l3"), ("fhn", "fhn_mlp_tanh_h128l3"), ("fhn", "fhn_dgm_h128l4")])
 def test_small_workspace_chunks(K, prob, name):
     from differential_equations_dnn_b200 import _cabi
     g = golden(name)
