@@ -15,7 +15,8 @@ from ._cabi import NetDesc, DgmkError  # noqa: F401
 
 _WS_CACHE: dict = {}
 # cap on the scratch a single call may hold; the steps chunk the batch to fit.
-WORKSPACE_CAP_BYTES = 48 << 30
+import os as _os
+WORKSPACE_CAP_BYTES = int(float(_os.environ.get("DGMK_WORKSPACE_GB", "48")) * (1 << 30))
 
 
 def _dev_f32(*tensors):
