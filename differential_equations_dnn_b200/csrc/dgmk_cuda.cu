@@ -65,6 +65,13 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const F f, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
 }
 
+// functors with a vec4(k) method: one thread = four consecutive hidden units of one row
+template <class F>
+__global__ void __launch_bounds__(EW_THREADS) ew4_kernel(const F f, int64_t n4) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += stride) f.vec4(k);
+}
+
 // deterministic second stage: out[i] (+)= sum_s part[s][i], FP64 accumulate, fixed order
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int nparts, int64_t n,
                                                               float* __restrict__ out) {
@@ -201,6 +208,18 @@ struct CudaBackend {
     if (blocks > cap) blocks = cap;
     ProfScope ps(PC_EW, st, 0.0, 0.0);
     ew_kernel<F><<<(unsigned)blocks, EW_THREADS, 0, st>>>(f, n);
+    post();
+  }
+  // n = rows * Hp elements, Hp a multiple of 32: four units per thread (16-byte accesses)
+  template <class F>
+  void ew4(const F& f, int64_t n) {
+    if (n <= 0) return;
+    const int64_t n4 = n / 4;
+    int64_t blocks = (n4 + EW_THREADS - 1) / EW_THREADS;
+    int64_t cap = (int64_t)sms * 32;
+    if (blocks > cap) blocks = cap;
+    ProfScope ps(PC_EW, st, 0.0, 0.0);
+    ew4_kernel<F><<<(unsigned)blocks, EW_THREADS, 0, st>>>(f, n4);
     post();
   }
   // C[M,N] (+)= A[M,K] B[K,N].  Shapes the tcgen05 tile covers (N % 128 == 0, K % 32 == 0, i.e.

@@ -13,7 +13,7 @@
 
 namespace dgmk {
 
-struct F4 { float x, y, z, w; };
+struct alignas(16) F4 { float x, y, z, w; };   // every F4 array in the workspace is 16-byte aligned
 
 // Where the coordinates of row r of a pass come from: up to 3 separate arrays
 // (heat companions X0 | XBD1 | XBD2) or one array walked in blocks with a stride
@@ -111,6 +111,33 @@ struct InputFwdFn {
 #pragma unroll
     for (int c = 0; c < CS::C; ++c) o[(int64_t)c * Hp] = y[c];
   }
+  // four consecutive units of one point (same arithmetic as operator(); 16-byte stores, the point's
+  // coordinates and the index division once per four elements); k = p * (Hp/4) + j/4
+  DGMK_HD void vec4(int64_t k) const {
+    const int q = Hp >> 2;
+    int64_t p = idiv(k, q); int j = (int)(k - p * q) * 4;
+    const float* x = xs.at(p);
+    const float x0 = x[0], x1 = (xs.d > 1) ? x[1] : 0.f;
+    float y[4][CS::C];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      F4 w = inb[j + u];
+      float a[CS::C];
+      a[0] = w.x * x0 + w.z;
+      if (xs.d > 1) a[0] += w.y * x1;
+#pragma unroll
+      for (int kk = 0; kk < CS::ND; ++kk) a[1 + kk] = (kk == 0) ? w.x : w.y;
+#pragma unroll
+      for (int qq = 0; qq < CS::NP; ++qq) a[1 + CS::ND + qq] = 0.f;
+      act_fwd<CS, ACT>(a, y[u]);
+    }
+    float* o = S0 + (p * CS::C) * Hp + j;
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) {
+      F4 v; v.x = y[0][c]; v.y = y[1][c]; v.z = y[2][c]; v.w = y[3][c];
+      *reinterpret_cast<F4*>(o + (int64_t)c * Hp) = v;
+    }
+  }
 };
 template <class CS, int ACT>
 struct InputRevFn {
@@ -129,6 +156,33 @@ struct InputRevFn {
     act_adj<CS, ACT>(yb, af, ab);
 #pragma unroll
     for (int c = 0; c < CS::C; ++c) AB[(p * CS::C + c) * ldab + j] = ab[c];
+  }
+  DGMK_HD void vec4(int64_t k) const {   // see InputFwdFn::vec4
+    const int q = Hp >> 2;
+    int64_t p = idiv(k, q); int j = (int)(k - p * q) * 4;
+    const F4 s0 = *reinterpret_cast<const F4*>(S0 + (p * CS::C) * Hp + j);
+    F4 sb[CS::C];
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) sb[c] = *reinterpret_cast<const F4*>(SB + (p * CS::C + c) * Hp + j);
+    float ab[4][CS::C];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      F4 w = inb[j + u];
+      float af[CS::C], yb[CS::C];
+      af[0] = u == 0 ? s0.x : (u == 1 ? s0.y : (u == 2 ? s0.z : s0.w));
+#pragma unroll
+      for (int kk = 0; kk < CS::ND; ++kk) af[1 + kk] = (kk == 0) ? w.x : w.y;
+#pragma unroll
+      for (int qq = 0; qq < CS::NP; ++qq) af[1 + CS::ND + qq] = 0.f;
+#pragma unroll
+      for (int c = 0; c < CS::C; ++c) yb[c] = u == 0 ? sb[c].x : (u == 1 ? sb[c].y : (u == 2 ? sb[c].z : sb[c].w));
+      act_adj<CS, ACT>(yb, af, ab[u]);
+    }
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) {
+      F4 v; v.x = ab[0][c]; v.y = ab[1][c]; v.z = ab[2][c]; v.w = ab[3][c];
+      *reinterpret_cast<F4*>(AB + (p * CS::C + c) * ldab + j) = v;
+    }
   }
 };
 
@@ -314,6 +368,18 @@ struct OutRevFn {
     float v = 0.f;
     for (int m = 0; m < o; ++m) v += UB[r * 4 + m] * outw[m * Hp + j];
     SB[i] = v;
+  }
+  DGMK_HD void vec4(int64_t k) const {   // four consecutive units of row r, same sums
+    const int q = Hp >> 2;
+    int64_t r = idiv(k, q); int j = (int)(k - r * q) * 4;
+    const F4 ub = *reinterpret_cast<const F4*>(UB + r * 4);
+    F4 v; v.x = 0.f; v.y = 0.f; v.z = 0.f; v.w = 0.f;
+    for (int m = 0; m < o; ++m) {
+      const float um = m == 0 ? ub.x : (m == 1 ? ub.y : (m == 2 ? ub.z : ub.w));
+      const F4 w = *reinterpret_cast<const F4*>(outw + m * Hp + j);
+      v.x += um * w.x; v.y += um * w.y; v.z += um * w.z; v.w += um * w.w;
+    }
+    *reinterpret_cast<F4*>(SB + r * (int64_t)Hp + j) = v;
   }
 };
 

@@ -172,7 +172,7 @@ struct Pipeline {
       bk.ew(fe, R);
       DGMK_ACT_SWITCH(n.in_act(), ACT, {
         InputFwdFn<CS, ACT> f; f.xs = pb.xs; f.inb = inb(); f.S0 = pb.S[0]; f.Hp = Hp;
-        bk.ew(f, R * Hp);
+        bk.ew4(f, R * Hp);
       })
       for (int l = 0; l < n.L; ++l) {
         if (!n.is_dgm()) {
@@ -225,7 +225,7 @@ struct Pipeline {
     float* SBp = rb.SBb;
     {
       OutRevFn f; f.UB = pb.UB; f.outw = c.Wp + c.pl.outw; f.SB = SBn; f.Hp = Hp; f.o = n.o;
-      bk.ew(f, M * Hp);
+      bk.ew4(f, M * Hp);
     }
     DGMK_CS_SWITCH(pb.cs, CS, {
       for (int l = n.L - 1; l >= 0; --l) {
@@ -269,7 +269,7 @@ struct Pipeline {
       }
       DGMK_ACT_SWITCH(n.in_act(), ACT, {
         InputRevFn<CS, ACT> f; f.inb = inb(); f.S0 = pb.S[0]; f.SB = SBn; f.AB = rb.AB; f.Hp = Hp; f.ldab = Hp;
-        bk.ew(f, R * Hp);
+        bk.ew4(f, R * Hp);
       })
       bk.wcolsum_acc(rb.AB, Hp, Hp, pb.E, M, Gp + c.pl.g_inb, c.part, c.part_n);
     })

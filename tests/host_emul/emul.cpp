@@ -15,6 +15,8 @@ struct HostBackend {
   int64_t hl_stride = 0;
   explicit HostBackend(void*) {}
   template <class F> void ew(const F& f, int64_t n) { for (int64_t i = 0; i < n; ++i) f(i); }
+  // the four-units-per-thread form of the same functors: exercise it on the host too
+  template <class F> void ew4(const F& f, int64_t n) { for (int64_t k = 0; k < n / 4; ++k) f.vec4(k); }
   // the fused GEMM + element-wise kernels are CUDA-only: the harness always takes the unfused route
   bool lane_ok(int, int) const { return false; }
   template <class CS, int ACT>
