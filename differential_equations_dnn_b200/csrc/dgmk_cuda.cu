@@ -411,10 +411,10 @@ struct CudaBackend {
     if (M <= 0) return;
     const int NE = Wt ? 4 : 1;
     int64_t max_blk = part_n / ((int64_t)NE * N);
-    if (max_blk > 512) max_blk = 512;
+    if (max_blk > 4096) max_blk = 4096;   // enough loads in flight to stream at HBM speed
     if (max_blk < 1) { if (!err) err = "internal: partial buffer too small"; return; }
     const int ctiles = (N + 127) / 128;
-    int64_t want = ((int64_t)sms * 16 + ctiles - 1) / ctiles;
+    int64_t want = ((int64_t)sms * 32 + ctiles - 1) / ctiles;
     int64_t by_rows = (M + 255) / 256;
     int64_t nblk = want < by_rows ? want : by_rows;
     if (nblk > max_blk) nblk = max_blk;
