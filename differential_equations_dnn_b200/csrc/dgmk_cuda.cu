@@ -411,7 +411,7 @@ struct CudaBackend {
     if (M <= 0) return;
     const int NE = Wt ? 4 : 1;
     int64_t max_blk = part_n / ((int64_t)NE * N);
-    if (max_blk > 4096) max_blk = 4096;   // enough loads in flight to stream at HBM speed
+    if (max_blk > 2048) max_blk = 2048;   // enough loads in flight to stream at HBM speed (second stage: nblk partials)
     if (max_blk < 1) { if (!err) err = "internal: partial buffer too small"; return; }
     const int ctiles = (N + 127) / 128;
     int64_t want = ((int64_t)sms * 32 + ctiles - 1) / ctiles;
