@@ -230,3 +230,28 @@ def test_cuda_graph_driver_matches_eager():
     assert np.allclose(eager[:15], graphed[:15], rtol=1e-4), (eager[:15], graphed[:15])
     assert abs(eager[-10:].mean() - graphed[-10:].mean()) <= 0.2 * abs(eager[-10:].mean())
     assert graphed[-1] < graphed[0]
+
+
+@pytest.mark.parametrize("kind", ["dgm", "mlp"])
+def test_eval_and_jets_hidden128(kind):
+    """Hidden size 128 through the module seams: value-only evaluation (fused forward kernels, ragged
+    row count) and the generic jet seam (channel set of 6: stays on the un-fused kernels) against the
+    FP64 jet oracle."""
+    from oracle import jets_np
+    from differential_equations_dnn_b200 import dgm_net, neural_networks
+    torch.manual_seed(5)
+    net = (dgm_net.DGM(2, 1, 128, 2) if kind == "dgm" else neural_networks.MLP(2, 1, 128, 2, activation="tanh")).cuda()
+    d = net.desc
+    spec = np.array([d.kind, d.input_dim, d.output_dim, d.hidden_size, d.num_layers, d.activation])
+    gen = torch.Generator().manual_seed(6)
+    X = torch.rand(1000 + 13, 2, generator=gen) * torch.tensor([np.pi, 3.0])
+    y64, J64, H64 = jets_np.jets_full(spec, net.flat_theta().double().cpu().numpy(), X.double().numpy())
+    with torch.no_grad():
+        y = net(X.cuda()).double().cpu().numpy()
+    assert rel(y, y64) < TOL
+    Xg = X.cuda().requires_grad_(True)
+    u = net(Xg)
+    (J,) = torch.autograd.grad(u, Xg, grad_outputs=torch.ones_like(u), create_graph=True)
+    assert rel(J.detach().double().cpu().numpy(), J64[:, 0, :]) < TOL
+    (Jx,) = torch.autograd.grad(J[:, 0], Xg, grad_outputs=torch.ones_like(J[:, 0]), create_graph=True)
+    assert rel(Jx[:, 0].detach().double().cpu().numpy(), H64[:, 0, 0, 0]) < TOL
