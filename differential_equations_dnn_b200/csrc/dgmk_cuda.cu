@@ -15,6 +15,9 @@
 namespace dgmk {
 
 constexpr int EW_THREADS = 256;
+#ifndef REV1_MINB_V
+#define REV1_MINB_V 6
+#endif
 
 // number of kernels this library has launched in this process (diagnostic: bench.py
 // reports it as gpu_launches)
@@ -72,25 +75,99 @@ __global__ void __launch_bounds__(EW_THREADS) ew4_kernel(const F f, int64_t n4) 
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += stride) f.vec4(k);
 }
 
-// deterministic second stage: out[i] (+)= sum_s part[s][i], FP64 accumulate, fixed order
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int nparts, int64_t n,
-                                                              float* __restrict__ out) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// deterministic second stage: out[(i / cols) * ldo + i % cols] += sum_p part[p][i], i < n.  FP64, fixed
+// order: blockDim = (32 outputs, S slices of the partials); a thread adds its slice with four
+// independent chains (loads in flight), the slices are combined in slice order.  (One thread per
+// output walking all partials -- the first version -- was latency-bound: 50-260 us per launch.)
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ part, int nparts, int64_t n,
+                                                               float* __restrict__ out, int cols, int64_t ldo) {
+  const int64_t i = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  const int S = blockDim.y, sl = threadIdx.y;
+  __shared__ double sm[32][33];
   double s = 0.0;
-  for (int p = 0; p < nparts; ++p) s += (double)part[(int64_t)p * n + i];
-  out[i] += (float)s;
+  if (i < n) {
+    const int chunk = (nparts + S - 1) / S;
+    const int p0 = sl * chunk, p1 = (p0 + chunk < nparts) ? p0 + chunk : nparts;
+    const float* q = part + (int64_t)p0 * n + i;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int p = p0;
+    for (; p + 4 <= p1; p += 4, q += 4 * n) {
+      const float v0 = __ldg(q), v1 = __ldg(q + n), v2 = __ldg(q + 2 * n), v3 = __ldg(q + 3 * n);
+      s0 += (double)v0; s1 += (double)v1; s2 += (double)v2; s3 += (double)v3;
+    }
+    for (; p < p1; ++p, q += n) s0 += (double)__ldg(q);
+    s = (s0 + s1) + (s2 + s3);
+  }
+  sm[sl][threadIdx.x] = s;
+  __syncthreads();
+  if (sl == 0 && i < n) {
+    double t = 0.0;
+    for (int k = 0; k < S; ++k) t += sm[k][threadIdx.x];
+    const int64_t r = i / cols, c = i - r * cols;
+    out[r * ldo + c] += (float)t;
+  }
 }
 
-// out[r * ldo + c] += sum_s part[s][r][c]  (r < rows, c < cols): strided variant
-__global__ void __launch_bounds__(256) reduce_partials_2d_kernel(const float* __restrict__ part, int nparts, int rows,
-                                                                 int cols, float* __restrict__ out, int64_t ldo) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * cols) return;
+// DgmRev1Fn (hidden size 128) that also forms grad[U | b] of the Z, G and H gates -- the input-map
+// adjoint of the three pre-activation cotangents it has just computed -- so that the weight-gradient
+// kernel has no A^T E work left.  The grid stride is a multiple of 128: a thread keeps its unit j.
+// part[blk][gate 0..2 = Z, G, H][e 0..2 = U[:,0], U[:,1], b][128]
+template <class CS>
+struct Rev1Sink {   // slot 3 = H, 1 = G, 0 = Z -> rows 2, 1, 0 of g
+  float x0, x1; float (*g)[3];
+  __device__ __forceinline__ void operator()(int slot, const float* ab) const { input_map_adj<CS>(ab, x0, x1, g[slot == 3 ? 2 : slot]); }
+};
+template <class F, class CS, int MINB>
+__global__ void __launch_bounds__(EW_THREADS, MINB) rev1_e_kernel(const F f, const XSrc xs, int64_t n, float* __restrict__ part) {
+  float g[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float* x = xs.at(i >> 7);
+    Rev1Sink<CS> sink;
+    sink.x0 = __ldg(x); sink.x1 = (xs.d > 1) ? __ldg(x + 1) : 0.f; sink.g = g;
+    f.run(i, sink);
+  }
+  __shared__ float sm[9][EW_THREADS];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) sm[k][threadIdx.x] = g[k / 3][k % 3];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+      part[((int64_t)blockIdx.x * 9 + k) * 128 + threadIdx.x] = sm[k][threadIdx.x] + sm[k][threadIdx.x + 128];
+  }
+}
+
+// second stage of the fused input-map gradients: part[p][g][e][128] -> out[e * ldo + gmap[g] * 128 + j] +=
+// sum_p, FP64, fixed order (slices of the partials per output, combined in slice order)
+__global__ void __launch_bounds__(1024) reduce_gate_e_kernel(const float* __restrict__ part, int nparts, int ngates, int gm0,
+                                                             int gm1, int gm2, float* __restrict__ out, int64_t ldo) {
+  const int o = blockIdx.x * 32 + threadIdx.x, S = blockDim.y, sl = threadIdx.y;
+  const int per = ngates * 384;
+  __shared__ double sm[32][33];
   double s = 0.0;
-  for (int p = 0; p < nparts; ++p) s += (double)part[(int64_t)p * rows * cols + i];
-  int r = i / cols, c = i - r * cols;
-  out[(int64_t)r * ldo + c] += (float)s;
+  if (o < per) {
+    const int chunk = (nparts + S - 1) / S;
+    const int p0 = sl * chunk, p1 = (p0 + chunk < nparts) ? p0 + chunk : nparts;
+    const float* q = part + (int64_t)p0 * per + o;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int p = p0;
+    for (; p + 4 <= p1; p += 4, q += 4 * per) {
+      const float v0 = __ldg(q), v1 = __ldg(q + per), v2 = __ldg(q + 2 * per), v3 = __ldg(q + 3 * per);
+      s0 += (double)v0; s1 += (double)v1; s2 += (double)v2; s3 += (double)v3;
+    }
+    for (; p < p1; ++p, q += per) s0 += (double)__ldg(q);
+    s = (s0 + s1) + (s2 + s3);
+  }
+  sm[sl][threadIdx.x] = s;
+  __syncthreads();
+  if (sl == 0 && o < per) {
+    double t = 0.0;
+    for (int k = 0; k < S; ++k) t += sm[k][threadIdx.x];
+    const int g = o / 384, e = (o / 128) % 3, j = o & 127;
+    const int gm = (g == 0) ? gm0 : (g == 1 ? gm1 : gm2);
+    out[(int64_t)e * ldo + gm * 128 + j] += (float)t;
+  }
 }
 
 // out-partials[blk][e][n] = sum_{r in block's row strip} Wt[r][e] * Mat[r][n]
@@ -265,8 +342,8 @@ struct CudaBackend {
   }
   // `units`: algorithmic HBM traffic of the launch in [M, 128] FP32 matrices (read + written)
   template <class EPI>
-  void lane_gemm(const float* X, int64_t ldx, const float* Wt, int64_t ldw, int64_t M, int ngates, const EPI& epi, double units) {
-    if (M <= 0) return;
+  int lane_gemm(const float* X, int64_t ldx, const float* Wt, int64_t ldw, int64_t M, int ngates, const EPI& epi, double units) {
+    if (M <= 0) return 0;
     ProfScope ps(PC_LANE, st, 2.0 * M * lg::NU * lg::KTOT * ngates, units * M * lg::KTOT * 4.0);
     // opt-in shared memory size: per function and per device
     static unsigned long long done_mask = 0;
@@ -292,6 +369,7 @@ struct CudaBackend {
     }
     lg::lane_gemm_kernel<EPI><<<(unsigned)grid, lg::NT, lg::SMEM_BYTES, st>>>(X, ldx, Wt, ldw, hl_stride, M, ngates, (int)c0, (int)c1, epi);
     post();
+    return (int)grid;
   }
   // one DGM layer forward: [Z|G|R] GEMM + gate activations + s*R, then the H GEMM + activation +
   // state update.  Wb = packed [4*Hp, Hp] (gate, out unit) x in unit.
@@ -313,6 +391,32 @@ struct CudaBackend {
       lane_gemm(AB4 + 3 * Hp, 4 * (int64_t)Hp, Wfh, Hp, M, 1, e, 6.0);   // read abar_H, R a-form, s, s bar; write abar_R, s bar
     } else if (!err) err = "internal: fused path called with an unsupported channel set";
   }
+  // DgmRev1Fn + grad[U | b] of the Z, G, H gates (hidden size 128; rows = collocation points)
+  template <class CS, class F>
+  void dgm_rev1_e(const F& f, const XSrc& xs, int64_t rows, float* outE, float* part, int64_t part_n) {
+    const int64_t n = rows * 128;
+    if (n <= 0) return;
+    if constexpr (!(CS::C == 1 || CS::C == 2 || CS::C == 4)) { if (!err) err = "internal: fused path called with an unsupported channel set"; return; } else {
+    int64_t blocks = (n + EW_THREADS - 1) / EW_THREADS;
+    // the value-only stage is light: more resident blocks (loads in flight) matter more than registers
+    constexpr int MINB = (CS::C == 1) ? REV1_MINB_V : 4;
+    int64_t cap = (int64_t)sms * MINB;   // one resident wave; a thread keeps its unit and its running sums
+    if (cap > part_n / (9 * 128)) cap = part_n / (9 * 128);
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) { if (!err) err = "internal: partial buffer too small"; return; }
+    {
+      ProfScope ps(PC_EW, st, 0.0, 0.0);
+      rev1_e_kernel<F, CS, MINB><<<(unsigned)blocks, EW_THREADS, 0, st>>>(f, xs, n, part);
+      post();
+    }
+    reduce_gate_e(part, (int)blocks, 3, 0, 1, 3, outE, 4 * 128);
+    }
+  }
+  void reduce_gate_e(const float* part, int nparts, int ngates, int gm0, int gm1, int gm2, float* out, int64_t ldo) {
+    ProfScope ps(PC_OTHER, st, 0.0, 0.0);
+    reduce_gate_e_kernel<<<(unsigned)((ngates * 384 + 31) / 32), dim3(32, nparts >= 512 ? 32 : 8), 0, st>>>(part, nparts, ngates, gm0, gm1, gm2, out, ldo);
+    post();
+  }
   // MLP hidden layer forward: GEMM + bias + activation
   template <class CS, int ACT>
   void mlp_fwd_fused(const float* Yp, float* G, const F4* ub, float* Yn, const float* Wb, int Hp, int64_t M) {
@@ -326,8 +430,13 @@ struct CudaBackend {
     lg::StoreEpi<false> e; e.C = C; e.ldc = ldc;
     lane_gemm(X, ldx, Wt, Hp, M, 1, e, 2.0);
   }
-  void reduce(const float* part, int nparts, int64_t n, float* out) {
-    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, nparts, n, out);
+  // out[(i / cols) * ldo + i % cols] += sum_p part[p][i]   (cols = 0: out[i])
+  void reduce(const float* part, int nparts, int64_t n, float* out, int cols = 0, int64_t ldo = 0) {
+    if (cols <= 0) { cols = (int)n; ldo = n; }
+    // slices: enough to keep every chain short, few enough that small partial counts are not split to nothing
+    const int S = nparts >= 512 ? 32 : (nparts >= 128 ? 16 : (nparts >= 16 ? 8 : 1));
+    ProfScope ps(PC_OTHER, st, 0.0, 0.0);
+    reduce_partials_kernel<<<(unsigned)((n + 31) / 32), dim3(32, S), 0, st>>>(part, nparts, n, out, cols, ldo);
     post();
   }
   // out[N,Kd] += A^T S ; if E: outE[e * ldoE + n] += sum_m A[m,n] E[m,e]  (fused in the same pass)
@@ -351,7 +460,7 @@ struct CudaBackend {
     splits = (M + rps - 1) / rps;
     float* PE = E ? part + splits * tile : nullptr;
     // warp-specialised tcgen05 kernel (A^T through tensor memory): one CTA per SM, one wave
-    const bool ws_ok = use_tc && fuse && E && N % tc::BM == 0 && Kd % tc::BN == 0 && lds == 128 && (lda == 128 || lda == 512);
+    const bool ws_ok = use_tc && fuse && N % tc::BM == 0 && Kd % tc::BN == 0 && lds == 128 && (lda == 128 || lda == 512);
     if (ws_ok) {
       // CTAs: one wave; each walks `nseg` segments of seg_rows rows and emits one partial per
       // segment, so the FP32 chains stay as short as with the many-splits streaming tile
@@ -369,7 +478,7 @@ struct CudaBackend {
       const int64_t seg_rows = ((M + ctas * nseg - 1) / (ctas * nseg) + 31) / 32 * 32;
       ctas = (M + seg_rows * nseg - 1) / (seg_rows * nseg);
       const int64_t nparts = (M + seg_rows - 1) / seg_rows;   // segments that contain rows (the rest is never written)
-      float* PEw = part + ctas * nseg * tile;
+      float* PEw = E ? part + ctas * nseg * tile : nullptr;
       dim3 gws(Kd / 128, N / 128, (unsigned)ctas);
       static unsigned long long done_mask = 0;
       int dev = 0;
@@ -384,8 +493,9 @@ struct CudaBackend {
       else wg::wgrad_ws_kernel<128, 128><<<gws, wg::NT, wg::SMEM_BYTES, st>>>(A, S, E, part, PEw, N, Kd, M, seg_rows, (int)nseg);
       post();
       reduce(part, (int)nparts, tile, out);
-      reduce_partials_2d_kernel<<<(unsigned)((4 * N + 255) / 256), 256, 0, st>>>(PEw, (int)(2 * nparts), 4, N, outE, ldoE);
-      post();
+      if (E) {
+        reduce(PEw, (int)(2 * nparts), 4 * (int64_t)N, outE, N, ldoE);
+      }
       return;
     }
     dim3 grid(Kd / BN, (N + GEMM_BM - 1) / GEMM_BM, (unsigned)splits);
@@ -402,12 +512,12 @@ struct CudaBackend {
     post();
     reduce(part, (int)splits, tile, out);
     if (E) {
-      reduce_partials_2d_kernel<<<(unsigned)((4 * N + 255) / 256), 256, 0, st>>>(PE, (int)splits, 4, N, outE, ldoE);
-      post();
+      reduce(PE, (int)splits, 4 * (int64_t)N, outE, N, ldoE);
     }
   }
+  // ldo > 0: out[e * ldo + n] (strided rows) instead of the packed [NE][N]
   void wcolsum_acc(const float* Mat, int64_t ldm, int N, const float* Wt, int64_t M, float* out, float* part,
-                   int64_t part_n) {
+                   int64_t part_n, int64_t ldo = 0) {
     if (M <= 0) return;
     const int NE = Wt ? 4 : 1;
     int64_t max_blk = part_n / ((int64_t)NE * N);
@@ -422,16 +532,21 @@ struct CudaBackend {
     int64_t rpb = (M + nblk - 1) / nblk;
     nblk = (M + rpb - 1) / rpb;
     dim3 grid(ctiles, (unsigned)nblk);
-    if (Wt) wcolsum_kernel<true><<<grid, 128, 0, st>>>(Mat, ldm, N, Wt, M, rpb, part);
-    else wcolsum_kernel<false><<<grid, 128, 0, st>>>(Mat, ldm, N, Wt, M, rpb, part);
-    post();
-    reduce(part, (int)nblk, (int64_t)NE * N, out);
+    {
+      ProfScope ps(PC_OTHER, st, 0.0, 0.0);
+      if (Wt) wcolsum_kernel<true><<<grid, 128, 0, st>>>(Mat, ldm, N, Wt, M, rpb, part);
+      else wcolsum_kernel<false><<<grid, 128, 0, st>>>(Mat, ldm, N, Wt, M, rpb, part);
+      post();
+    }
+    if (ldo > 0) reduce(part, (int)nblk, (int64_t)NE * N, out, N, ldo);
+    else reduce(part, (int)nblk, (int64_t)NE * N, out);
   }
   void rowdot(const float* S, int64_t lds, const float* W, const float* b, float* U, int64_t M, int Hp, int o, int C) {
     if (M <= 0) return;
     int64_t blocks = (M + 7) / 8;
     int64_t cap = (int64_t)sms * 16;
     if (blocks > cap) blocks = cap;
+    ProfScope ps(PC_OTHER, st, 0.0, 0.0);
     rowdot_kernel<<<(unsigned)blocks, 256, 0, st>>>(S, lds, W, b, U, M, Hp, o, C);
     post();
   }
@@ -477,7 +592,7 @@ unsigned long long dgmk_launch_count(void) { return dgmk::g_launches; }
 // around every launch; dgmk_profile(0) stops.  dgmk_profile_read(cls, ...) synchronises the
 // recorded events and returns the class's summed duration [ms], launches, algorithmic flops and
 // bytes.  Classes: 0 weight gradient (wgrad_ws), 1 fused units-on-lanes GEMM + element-wise kernels,
-// 2 streaming tcgen05 / FFMA GEMM tiles, 3 stand-alone element-wise kernels.
+// 2 streaming tcgen05 / FFMA GEMM tiles, 3 stand-alone element-wise kernels, 4 reductions / output layer.
 void dgmk_profile(int on) {
   using namespace dgmk;
   if (on) {

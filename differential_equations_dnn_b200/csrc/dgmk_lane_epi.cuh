@@ -6,7 +6,8 @@
 //   Const  init(gate, j)                          per-thread constants (input-map weights)
 //   void   tile(t, k, row0, M, lane)              once per tile: coordinates of the thread's EPI_ROWS rows
 //   void   prefetch(pre, t, k, row0, cg, M)       ISSUE every global load group cg needs
-//   void   apply(pre, k, row0, M, acc)            acc[q] = W[j,:] . X[row0 + q,:]; math + stores
+//   void   apply(pre, st, t, cg, k, row0, M, acc) acc[q] = W[j,:] . X[row0 + q,:]; math + stores
+//   State / finish(st, k, slot)                   per-thread state across tiles, flushed at the end
 //
 // The split matters: only 8 epilogue warps (2 per scheduler) live on an SM, so latency has to be
 // hidden inside each thread: the loads of a group are in flight while the previous group is being
@@ -78,6 +79,8 @@ struct DgmFwd1Epi {
   static constexpr int C = CS::C;
   struct Const { F4 u; int gate, j; };
   using Tile = XTile<C>;
+  struct State {};
+  __device__ __forceinline__ void finish(const State&, const Const&, int) const {}
   struct Pre { XPre<C> x; float s[8]; };
   __device__ __forceinline__ Const init(int gate, int j) const { Const k; k.u = ub[gate * HP + j]; k.gate = gate; k.j = j; return k; }
   __device__ __forceinline__ void tile(Tile& t, const Const&, int64_t row0, int64_t M, int lane) const { t.load(xs, row0, M, lane); }
@@ -90,7 +93,7 @@ struct DgmFwd1Epi {
     }
   }
   template <bool FULL>
-  __device__ __forceinline__ void apply(const Pre& p, const Const& k, int64_t row0, int64_t M, const float (&acc)[8]) const {
+  __device__ __forceinline__ void apply(const Pre& p, State& st, const Tile& t, int cg, const Const& k, int64_t row0, int64_t M, const float (&acc)[8]) const {
     float af[8], sr[8];   // a-form rows and (R gate) s*R rows of the whole group
 #pragma unroll
     for (int pp = 0; pp < 8 / C; ++pp) {
@@ -131,6 +134,8 @@ struct DgmFwd2Epi {
   static constexpr int C = CS::C;
   struct Const { F4 u; int j; };
   using Tile = XTile<C>;
+  struct State {};
+  __device__ __forceinline__ void finish(const State&, const Const&, int) const {}
   struct Pre { XPre<C> x; float z[8], g[8], s[8]; };
   __device__ __forceinline__ Const init(int, int j) const { Const k; k.u = ub[3 * HP + j]; k.j = j; return k; }
   __device__ __forceinline__ void tile(Tile& t, const Const&, int64_t row0, int64_t M, int lane) const { t.load(xs, row0, M, lane); }
@@ -147,7 +152,7 @@ struct DgmFwd2Epi {
     }
   }
   template <bool FULL>
-  __device__ __forceinline__ void apply(const Pre& p, const Const& k, int64_t row0, int64_t M, const float (&acc)[8]) const {
+  __device__ __forceinline__ void apply(const Pre& p, State& st, const Tile& t, int cg, const Const& k, int64_t row0, int64_t M, const float (&acc)[8]) const {
     float af[8], sn[8];
 #pragma unroll
     for (int pp = 0; pp < 8 / C; ++pp) {
@@ -184,13 +189,15 @@ struct MlpActEpi {
   static constexpr int C = CS::C;
   struct Const { float b; int j; };
   using Tile = NoTile;
+  struct State {};
+  __device__ __forceinline__ void finish(const State&, const Const&, int) const {}
   struct Pre {};
   __device__ __forceinline__ Const init(int, int j) const { Const k; k.b = ub[j].z; k.j = j; return k; }
   __device__ __forceinline__ void tile(Tile&, const Const&, int64_t, int64_t, int) const {}
   template <bool FULL>
   __device__ __forceinline__ void prefetch(Pre&, const Tile&, const Const&, int64_t, int, int64_t) const {}
   template <bool FULL>
-  __device__ __forceinline__ void apply(const Pre&, const Const& k, int64_t row0, int64_t M, const float (&acc)[8]) const {
+  __device__ __forceinline__ void apply(const Pre&, State&, const Tile&, int, const Const& k, int64_t row0, int64_t M, const float (&acc)[8]) const {
     float af[8], yo[8];
 #pragma unroll
     for (int pp = 0; pp < 8 / C; ++pp) {
@@ -221,6 +228,8 @@ struct DgmRev2Epi {
   static constexpr int C = CS::C;
   struct Const { int j; };
   using Tile = NoTile;
+  struct State {};
+  __device__ __forceinline__ void finish(const State&, const Const&, int) const {}
   struct Pre { float afr[8], s[8], sbar[8]; };
   __device__ __forceinline__ Const init(int, int j) const { Const k; k.j = j; return k; }
   __device__ __forceinline__ void tile(Tile&, const Const&, int64_t, int64_t, int) const {}
@@ -234,8 +243,11 @@ struct DgmRev2Epi {
       p.sbar[q] = SBp[r * HP + k.j];   // read-modify-write by this thread only
     }
   }
+  // (grad[U_r | b_r] = abar_R^T E is NOT formed here: the coordinates and running sums it needs cost
+  // ~10 registers the prefetch ring lives on -- measured +4 ms per step; a column-sum pass over abar_R
+  // does it for 1 unit of HBM traffic instead)
   template <bool FULL>
-  __device__ __forceinline__ void apply(const Pre& p, const Const& k, int64_t row0, int64_t M, const float (&acc)[8]) const {
+  __device__ __forceinline__ void apply(const Pre& p, State&, const Tile&, int, const Const& k, int64_t row0, int64_t M, const float (&acc)[8]) const {
     float abo[8], sbo[8];
 #pragma unroll
     for (int pp = 0; pp < 8 / C; ++pp) {

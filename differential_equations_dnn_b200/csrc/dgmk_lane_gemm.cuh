@@ -157,7 +157,9 @@ struct StoreEpi {
   float* C; int64_t ldc;
   struct Const { int col; };
   struct Tile {};
+  struct State {};
   struct Pre { float old[8]; };
+  __device__ __forceinline__ void finish(const State&, const Const&, int) const {}
   __device__ __forceinline__ Const init(int gate, int j) const { Const k; k.col = gate * NU + j; return k; }
   __device__ __forceinline__ void tile(Tile&, const Const&, int64_t, int64_t, int) const {}
   template <bool FULL>
@@ -169,7 +171,7 @@ struct StoreEpi {
   }
   // a[q] = D[j, row0 + q], q = 0..7; rows >= M are padding
   template <bool FULL>
-  __device__ __forceinline__ void apply(const Pre& p, const Const& k, int64_t row0, int64_t M, const float (&a)[8]) const {
+  __device__ __forceinline__ void apply(const Pre& p, State&, const Tile&, int, const Const& k, int64_t row0, int64_t M, const float (&a)[8]) const {
     float* c = C + row0 * ldc + k.col;
 #pragma unroll
     for (int q = 0; q < 8; ++q)
@@ -371,6 +373,7 @@ __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restric
       // loads of group 1 go out, while group 1 is computed those of the next tile's group 0.
       typename EPI::Tile et, et_next;
       typename EPI::Pre pre[EPI_GROUPS];
+      typename EPI::State est{};   // per-thread state that lives across tiles (e.g. gradient partial sums)
       uint32_t i = 0;
       LG_PROF_DECL;
       if (grp < ntiles) {
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restric
               epi.template prefetch<FULL>(pre[0], et_next, ek, nrow0, 0, M);
             }
             const float a8[8] = {a[cg * 8], a[cg * 8 + 1], a[cg * 8 + 2], a[cg * 8 + 3], a[cg * 8 + 4], a[cg * 8 + 5], a[cg * 8 + 6], a[cg * 8 + 7]};
-            epi.template apply<FULL>(pre[cg], ek, row0 + cg * 8, M, a8);
+            epi.template apply<FULL>(pre[cg], est, et, cg, ek, row0 + cg * 8, M, a8);
           }
         };
         if (row0 + EPI_ROWS <= M && (!has_next || nrow0 + EPI_ROWS <= M)) groups(FullTag<true>{});
@@ -425,6 +428,7 @@ __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restric
         et = et_next;
         LG_ADD(2, t2);
       }
+      epi.finish(est, ek, (int)blockIdx.x * (EPI_WARPS / 4) + part);
       if (warp == W_EPI) { LG_PROF_OUT(24); }
     }
    }

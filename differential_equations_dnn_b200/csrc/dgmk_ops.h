@@ -228,6 +228,16 @@ DGMK_HD void add_input_map(float* a, const F4& u, const float* x, int d) {
 #pragma unroll
   for (int k = 0; k < CS::ND; ++k) a[1 + k] += (k == 0) ? u.x : u.y;
 }
+// adjoint of add_input_map for one point: g[0..1] += grad U[:, 0..1], g[2] += grad b.  Same sums as
+// abar^T E over the point's rows (E: ExtInputFn), with the structural zeros and ones of E folded in
+template <class CS>
+DGMK_HD void input_map_adj(const float* ab, float x0, float x1, float* g) {
+  g[0] = fmaf(ab[0], x0, g[0]);
+  g[1] = fmaf(ab[0], x1, g[1]);
+  g[2] += ab[0];
+  if (CS::ND > 0) g[0] += ab[1];
+  if (CS::ND > 1) g[1] += ab[2];
+}
 // stage 1: Z, G, R = act(W s + U x + b) in place (a-form), SR = s * R
 template <class CS, int ACT>
 struct DgmFwd1Fn {
@@ -295,7 +305,12 @@ struct DgmFwd2Fn {
 template <class CS, int ACT>
 struct DgmRev1Fn {
   const float* A4; const float* S; const float* SBn; float* AB4; float* SBp; int Hp;
-  DGMK_HD void operator()(int64_t i) const {
+  struct NoSink { DGMK_HD void operator()(int, const float*) const {} };
+  DGMK_HD void operator()(int64_t i) const { run(i, NoSink{}); }
+  // sink(slot, ab): called with each pre-activation cotangent (slot 3 = H, 1 = G, 0 = Z) as soon as it
+  // exists (the CUDA backend's fused variant forms grad[U | b] from them: input_map_adj)
+  template <class Sink>
+  DGMK_HD void run(int64_t i, Sink&& sink) const {
     int64_t p = idiv(i, Hp); int j = (int)(i - p * Hp);
     const int64_t ld = 4 * (int64_t)Hp;
     const float* row = A4 + (p * CS::C) * ld + j;
@@ -318,16 +333,19 @@ struct DgmRev1Fn {
     act_adj<CS, ACT>(yb, afh, ab);
 #pragma unroll
     for (int c = 0; c < CS::C; ++c) orow[c * ld + 3 * Hp] = ab[c];
+    sink(3, ab);
     prod_adj<CS, false>(nb, h, yb);    // -(Gbar)
 #pragma unroll
     for (int c = 0; c < CS::C; ++c) yb[c] = -yb[c];
     act_adj<CS, ACT>(yb, afg, ab);
 #pragma unroll
     for (int c = 0; c < CS::C; ++c) orow[c * ld + Hp] = ab[c];
+    sink(1, ab);
     prod_adj<CS, false>(nb, s, yb);    // Zbar
     act_adj<CS, ACT>(yb, afz, ab);
 #pragma unroll
     for (int c = 0; c < CS::C; ++c) orow[c * ld] = ab[c];
+    sink(0, ab);
     prod_adj<CS, false>(nb, z, yb);    // direct path to s
 #pragma unroll
     for (int c = 0; c < CS::C; ++c) SBp[sb + (int64_t)c * Hp] = yb[c];

@@ -239,15 +239,22 @@ struct Pipeline {
           if (bk.lane_ok(Hp, CS_V)) bk.lane_store(rb.AB, Hp, c.Wp + c.pl.wf[l], SBp, Hp, Hp, M);
           else bk.gemm_nn(rb.AB, Hp, c.Wp + c.pl.wb[l], Hp, c.Wp + c.pl.wf[l], Hp, SBp, Hp, M, Hp, Hp, false);
         } else {
+          // fused path (hidden size 128): grad[U | b] is formed where the pre-activation cotangents are
+          // produced (input_map_adj), so the weight-gradient passes carry no A^T E work
+          const bool fe = bk.lane_ok(Hp, pb.cs);
+          float* gub = Gp + c.pl.g_ub[l];
           DGMK_GACT_SWITCH(n.gate_act(), ACT, {
             DgmRev1Fn<CS, ACT> f; f.A4 = pb.G[l]; f.S = pb.S[l]; f.SBn = SBn; f.AB4 = rb.AB; f.SBp = SBp; f.Hp = Hp;
-            bk.ew(f, R * Hp);
+            if (fe) bk.template dgm_rev1_e<CS>(f, pb.xs, R, gub, c.part, c.part_n);
+            else bk.ew(f, R * Hp);
           })
           // (s*R)bar = abar_H W_h, then the R-gate adjoint (one kernel on the fused path)
-          if (bk.lane_ok(Hp, pb.cs)) {
+          if (fe) {
             DGMK_GACT_SWITCH(n.gate_act(), ACT, {
               bk.template dgm_rev2_fused<CS, ACT>(pb.G[l], pb.S[l], rb.AB, SBp, c.Wp + c.pl.wfh[l], Hp, M);
             })
+            // grad[U_r | b_r] = abar_R^T E: a column-sum pass over abar_R (1 unit)
+            bk.wcolsum_acc(rb.AB + 2 * Hp, 4 * Hp, Hp, pb.E, M, gub + 2 * Hp, c.part, c.part_n, 4 * Hp);
           } else {
             bk.gemm_nn(rb.AB + 3 * Hp, 4 * Hp, c.Wp + c.pl.wb[l] + (int64_t)3 * Hp * Hp, Hp, c.Wp + c.pl.wfh[l], Hp, rb.SRB, Hp, M, Hp,
                        Hp, false);
@@ -258,12 +265,11 @@ struct Pipeline {
           }
           // s bar += [abar_Z | abar_G | abar_R] [W_z; W_g; W_r]
           bk.gemm_nn(rb.AB, 4 * Hp, c.Wp + c.pl.wb[l], Hp, c.Wp + c.pl.wf[l], 3 * Hp, SBp, Hp, M, Hp, 3 * Hp, true);
-          // weight gradients
-          // weight gradients; grad[U | b] = Abar^T E rides along in the same passes
-          bk.gemm_tn_acc(rb.AB, 4 * Hp, pb.S[l], Hp, Gp + c.pl.g_w[l], 3 * Hp, Hp, M, pb.E, Gp + c.pl.g_ub[l], 4 * Hp,
-                         c.part, c.part_n);
-          bk.gemm_tn_acc(rb.AB + 3 * Hp, 4 * Hp, pb.SR[l], Hp, Gp + c.pl.g_w[l] + (int64_t)3 * Hp * Hp, Hp, Hp, M, pb.E,
-                         Gp + c.pl.g_ub[l] + 3 * Hp, 4 * Hp, c.part, c.part_n);
+          // weight gradients; off the fused path grad[U | b] = Abar^T E rides along in the same passes
+          const float* Ew = fe ? nullptr : pb.E;
+          bk.gemm_tn_acc(rb.AB, 4 * Hp, pb.S[l], Hp, Gp + c.pl.g_w[l], 3 * Hp, Hp, M, Ew, gub, 4 * Hp, c.part, c.part_n);
+          bk.gemm_tn_acc(rb.AB + 3 * Hp, 4 * Hp, pb.SR[l], Hp, Gp + c.pl.g_w[l] + (int64_t)3 * Hp * Hp, Hp, Hp, M, Ew, gub + 3 * Hp,
+                         4 * Hp, c.part, c.part_n);
         }
         float* t = SBn; SBn = SBp; SBp = t;
       }

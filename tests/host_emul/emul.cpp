@@ -23,6 +23,8 @@ struct HostBackend {
   void dgm_fwd_fused(const dgmk::XSrc&, const float*, float*, const dgmk::F4*, float*, float*, const float*, int, int64_t) {}
   template <class CS, int ACT>
   void dgm_rev2_fused(const float*, const float*, float*, float*, const float*, int, int64_t) {}
+  template <class CS, class F>
+  void dgm_rev1_e(const F&, const dgmk::XSrc&, int64_t, float*, float*, int64_t) {}
   template <class CS, int ACT>
   void mlp_fwd_fused(const float*, float*, const dgmk::F4*, float*, const float*, int, int64_t) {}
   void lane_store(const float*, int64_t, const float*, float*, int64_t, int, int64_t) {}
@@ -52,7 +54,7 @@ struct HostBackend {
     for (size_t i = 0; i < acc.size(); ++i) out[i] += (float)acc[i];
     if (E) for (int e = 0; e < 4; ++e) for (int n = 0; n < N; ++n) outE[e * ldoE + n] += (float)eacc[(size_t)e * N + n];
   }
-  void wcolsum_acc(const float* Mat, int64_t ldm, int N, const float* Wt, int64_t M, float* out, float*, int64_t) {
+  void wcolsum_acc(const float* Mat, int64_t ldm, int N, const float* Wt, int64_t M, float* out, float*, int64_t, int64_t ldo = 0) {
     int NE = Wt ? 4 : 1;
     std::vector<double> acc((size_t)NE * N, 0.0);
     for (int64_t r = 0; r < M; ++r)
@@ -60,7 +62,7 @@ struct HostBackend {
         double w = Wt ? Wt[r * 4 + e] : 1.0;
         for (int n = 0; n < N; ++n) acc[(size_t)e * N + n] += w * Mat[r * ldm + n];
       }
-    for (size_t i = 0; i < acc.size(); ++i) out[i] += (float)acc[i];
+    for (int e = 0; e < NE; ++e) for (int n = 0; n < N; ++n) out[(ldo > 0 ? e * ldo : (int64_t)e * N) + n] += (float)acc[(size_t)e * N + n];
   }
   void rowdot(const float* S, int64_t lds, const float* W, const float* b, float* U, int64_t M, int Hp, int o, int C) {
     for (int64_t r = 0; r < M; ++r)

@@ -41,13 +41,15 @@ struct NoStoreEpi {
   float* C; int64_t ldc;
   struct Const { int col; };
   struct Tile {};
+  struct State {};
   struct Pre {};
+  __device__ __forceinline__ void finish(const State&, const Const&, int) const {}
   __device__ __forceinline__ Const init(int gate, int j) const { Const k; k.col = gate * 128 + j; return k; }
   __device__ __forceinline__ void tile(Tile&, const Const&, int64_t, int64_t, int) const {}
   template <bool FULL>
   __device__ __forceinline__ void prefetch(Pre&, const Tile&, const Const&, int64_t, int, int64_t) const {}
   template <bool FULL>
-  __device__ __forceinline__ void apply(const Pre&, const Const& k, int64_t row0, int64_t M, const float (&a)[8]) const {
+  __device__ __forceinline__ void apply(const Pre&, State&, const Tile&, int, const Const& k, int64_t row0, int64_t M, const float (&a)[8]) const {
     float s = 0.f;
 #pragma unroll
     for (int q = 0; q < 8; ++q) s += a[q];

@@ -98,6 +98,12 @@ int main() {
         { long long h[32]; CK(cudaMemcpyFromSymbol(h, dgmk::wg::g_wg_prof, sizeof(h))); double n = (double)h[30];
           printf("   cycles/chunk (%d chunks): loader[issue_loads %.0f wait_aempty %.0f split+st %.0f E %.0f] stager[issue_loads %.0f wait_bempty %.0f split+sts %.0f] mma[wait_tempty %.0f wait_afull %.0f wait_bfull %.0f issue %.0f] drain[wait_tfull %.0f drain %.0f]\n",
                  (int)n, h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[8] / n, h[9] / n, h[10] / n, h[26] / n, h[27] / n, h[28] / n, h[29] / n, h[24] / n, h[25] / n); }
+        // the same launch without the A^T E side product (the fused path forms grad[U | b] elsewhere)
+        ms = time_ms([&] { dgmk::wg::wgrad_ws_kernel<512, 512><<<g3, dgmk::wg::NT, dgmk::wg::SMEM_BYTES>>>(C, A, nullptr, P, nullptr, 384, 128, M, rps2, 1); }, 10);
+        printf("wgrad ZGR warp-specialised, %d splits, no E: %.3f ms  %.2f TFLOP/s\n", splits2, ms, 2.0 * M * 384 * 128 / ms * 1e-9);
+        { long long h[32]; CK(cudaMemcpyFromSymbol(h, dgmk::wg::g_wg_prof, sizeof(h))); double n = (double)h[30];
+          printf("   cycles/chunk (%d chunks): loader[issue_loads %.0f wait_aempty %.0f split+st %.0f E %.0f] stager[issue_loads %.0f wait_bempty %.0f split+sts %.0f] mma[wait_tempty %.0f wait_afull %.0f wait_bfull %.0f issue %.0f] drain[wait_tfull %.0f drain %.0f]\n",
+                 (int)n, h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[8] / n, h[9] / n, h[10] / n, h[26] / n, h[27] / n, h[28] / n, h[29] / n, h[24] / n, h[25] / n); }
         dim3 g4(1, 1, splits2 * 3 > 148 ? 148 : splits2 * 3);
         int64_t rps3 = ((M + g4.z - 1) / g4.z + 31) / 32 * 32;
         ms = time_ms([&] { dgmk::wg::wgrad_ws_kernel<512, 512><<<g4, dgmk::wg::NT, dgmk::wg::SMEM_BYTES>>>(C, A, E, P, PE, 128, 128, M, rps3, 1); }, 10);
