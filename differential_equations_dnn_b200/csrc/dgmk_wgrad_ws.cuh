@@ -26,11 +26,19 @@
 //
 // 20 warps: 0-7 A loaders (thread = TMEM lane 32*(w%4)+lane, rows 16*(w/4).. of every chunk), 8-11 S
 // stagers, 12-19 drain (warp w: lanes 32*(w%4).., columns 64*((w-12)/4)..); setmaxnreg moves
-// registers from the loaders to the drain warps (64 accumulators each).  Warp 12 is also the MMA
-// issuer: chunk c+2 reuses the accumulator buffer of chunk c, so it can only be issued once chunk c
-// is drained -- exactly the point where that warp stands in its loop.  Per-role cycle counters
+// registers from the loaders to the drain warps (64 accumulators each).  Per-role cycle counters
 // (tools/microbench/bench_tc.cu) showed a single loader warp per lane quarter to be the critical
 // path (load wait + split + tcgen05.st + A^T E = 1670 cycles per chunk); two halve it.
+//
+// Who issues the MMAs (template flag SEP):
+//   SEP = false  warp 12 (a drain warp): chunk c+2 reuses the accumulator buffer of chunk c, so it is
+//                issued where that warp stands once chunk c is drained.  But tcgen05.mma issue blocks on
+//                the tensor pipe's short queue (12 MMAs = ~790 cycles, the math time itself), so the
+//                pipe idles while warp 12 drains and polls: ~1580 cycles per chunk (measured).
+//   SEP = true   a sixth warpgroup (warp 20 issues, 21-23 idle) owns the MMAs, so chunk c+1 runs while
+//                chunk c is drained.  No A^T E side product in this variant (its loaders give 8
+//                registers per thread to the new warpgroup): the fused DGM path forms grad[U | b]
+//                elsewhere (input_map_adj) and passes PE = nullptr.
 // grid = (Kd/128, N/128, splits).
 #pragma once
 #include "dgmk_gemm_tc_tn.cuh"
@@ -52,10 +60,13 @@ __device__ long long g_wg_prof[32];
 #define WG_DECL
 #define WG_OUT(base)
 #endif
-constexpr int NT = 20 * 32;
-constexpr int W_STAGE = 8, W_DRAIN = 12;
+constexpr int NT = 20 * 32;                        // SEP = false
+constexpr int NT_SEP = 24 * 32;                    // SEP = true
+constexpr int W_STAGE = 8, W_DRAIN = 12, W_ISSUE = 20;
 constexpr int HR = KC / 2;                         // rows of a chunk per loader warp
 constexpr int REGS_LOAD = 72, REGS_STAGE = 96, REGS_DRAIN = 120;   // 256*72 + 128*96 + 256*120 = 640*96
+// SEP: launch allocation 768 x 80 = 61440 = 256*64 + 128*96 + 256*112 + 128*32
+constexpr int REGS_LOAD_SEP = 64, REGS_DRAIN_SEP = 112, REGS_ISSUE_SEP = 32;
 constexpr int NB = 3;                              // S ring stages
 constexpr int STAGE_BYTES = 2 * TN_OPER_BYTES;     // hi | lo
 constexpr int BAR_OFF = NB * STAGE_BYTES;
@@ -92,8 +103,8 @@ __device__ __forceinline__ float ldg_pinned(const float* p) {   // issued where 
 // LDA / LDS: leading dimensions of A and S, compile-time so that the 32 row loads of a chunk are one
 // base register plus immediates (with run-time strides the address arithmetic alone -- ~6
 // instructions per load in a warp that has a scheduler almost to itself -- cost 1700 cycles a chunk)
-template <int LDA, int LDS>
-__global__ void __launch_bounds__(NT, 1) wgrad_ws_kernel(const float* __restrict__ A,
+template <int LDA, int LDS, bool SEP>
+__global__ void __launch_bounds__(SEP ? NT_SEP : NT, 1) wgrad_ws_kernel(const float* __restrict__ A,
                                                          const float* __restrict__ S,
                                                          const float* __restrict__ E, float* __restrict__ P,
                                                          float* __restrict__ PE, int N, int Kd, int64_t M,
@@ -113,7 +124,7 @@ __global__ void __launch_bounds__(NT, 1) wgrad_ws_kernel(const float* __restrict
   const int64_t me = (mb + rows_per_split < M) ? mb + rows_per_split : M;
   const int64_t nchunks = (me > mb) ? (me - mb + KC - 1) / KC : 0;
   const int64_t cps = seg_rows / KC;                 // chunks per segment
-  const bool do_e = (PE != nullptr) && (blockIdx.x == 0);
+  const bool do_e = !SEP && (PE != nullptr) && (blockIdx.x == 0);
 
   if (warp == W_DRAIN) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tctn::smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
@@ -138,7 +149,8 @@ __global__ void __launch_bounds__(NT, 1) wgrad_ws_kernel(const float* __restrict
   const uint32_t tmem = *tmem_slot;
 
   if (warp < W_STAGE) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS_LOAD));
+    if constexpr (SEP) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS_LOAD_SEP));
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS_LOAD));
     // ================================ A loaders: global -> hi / lo -> TMEM ===================
     // Two register sets (even / odd chunks) keep one chunk of loads in flight while the previous
     // one is split and stored; they must stay in registers (a spilled prefetch register turns
@@ -233,7 +245,8 @@ __global__ void __launch_bounds__(NT, 1) wgrad_ws_kernel(const float* __restrict
     }
     if (warp == 0) { WG_OUT(0); }
   } else if (warp < W_DRAIN) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS_STAGE));
+    if constexpr (SEP) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REGS_STAGE));   // launch allocation: 80
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS_STAGE));
     // ================================ S stagers: global -> hi / lo -> shared ring ==============
     const int sw = warp - W_STAGE;                       // rows sw + 4 q of the chunk, columns lane*4 ..
     const float* sbase = S + j0 + lane * 4;
@@ -282,12 +295,6 @@ __global__ void __launch_bounds__(NT, 1) wgrad_ws_kernel(const float* __restrict
     }
     if (warp == W_STAGE) { WG_OUT(8); }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REGS_DRAIN));
-    // ================================ drain: chunk results -> RN registers; warp 12: MMA issue ===
-    const int quarter = warp & 3, half = (warp - W_DRAIN) >> 2;
-    float acc[HALF];
-#pragma unroll
-    for (int j = 0; j < HALF; ++j) acc[j] = 0.f;
     WG_DECL;
     // warp-uniform; one elected lane issues the 12 MMAs of chunk c and the three commits
     auto issue = [&](int64_t c) {
@@ -328,34 +335,51 @@ __global__ void __launch_bounds__(NT, 1) wgrad_ws_kernel(const float* __restrict
       __syncwarp();
       WG_ADD(5, t3);
     };
-    if (warp == W_DRAIN) {
-      if (nchunks > 0) issue(0);
-      if (nchunks > 1) issue(1);
-    }
-    for (int64_t c = 0; c < nchunks; ++c) {
-      const int buf = (int)(c & 1);
-      WG_T(t0);
-      tctn::mbar_wait(T_FULL + 8 * buf, (uint32_t)((c >> 1) & 1));
-      WG_ADD(0, t0);
-      WG_T(t1);
-      tctn::drain_half(tmem + TM_ACC, buf, quarter, half, acc);   // fences inside
-      mbar_arrive(T_EMPTY + 8 * buf);
-      WG_ADD(1, t1);
-      if (warp == W_DRAIN && c + 2 < nchunks) issue(c + 2);
-      if ((c + 1) % cps == 0 || c + 1 == nchunks) {   // segment complete: this thread owns output row
-        // i0 + quarter*32 + lane, columns j0 + half*64 .. of the segment's partial
-        float* prow = P + ((int64_t)blockIdx.z * nseg + c / cps) * N * Kd + (int64_t)(i0 + quarter * 32 + lane) * Kd + j0 + half * HALF;
+    if (warp < W_ISSUE) {
+      if constexpr (SEP) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REGS_DRAIN_SEP));
+      else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REGS_DRAIN));
+      // ============================== drain: chunk results -> RN registers (!SEP: warp 12 also issues) ===
+      const int quarter = warp & 3, half = (warp - W_DRAIN) >> 2;
+      float acc[HALF];
 #pragma unroll
-        for (int q = 0; q < HALF / 4; ++q) {
-          *reinterpret_cast<float4*>(prow + q * 4) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-          acc[4 * q] = 0.f; acc[4 * q + 1] = 0.f; acc[4 * q + 2] = 0.f; acc[4 * q + 3] = 0.f;
+      for (int j = 0; j < HALF; ++j) acc[j] = 0.f;
+      if (!SEP && warp == W_DRAIN) {
+        if (nchunks > 0) issue(0);
+        if (nchunks > 1) issue(1);
+      }
+      for (int64_t c = 0; c < nchunks; ++c) {
+        const int buf = (int)(c & 1);
+        WG_T(t0);
+        tctn::mbar_wait(T_FULL + 8 * buf, (uint32_t)((c >> 1) & 1));
+        WG_ADD(0, t0);
+        WG_T(t1);
+        tctn::drain_half(tmem + TM_ACC, buf, quarter, half, acc);   // fences inside
+        mbar_arrive(T_EMPTY + 8 * buf);
+        WG_ADD(1, t1);
+        if (!SEP && warp == W_DRAIN && c + 2 < nchunks) issue(c + 2);
+        if ((c + 1) % cps == 0 || c + 1 == nchunks) {   // segment complete: this thread owns output row
+          // i0 + quarter*32 + lane, columns j0 + half*64 .. of the segment's partial
+          float* prow = P + ((int64_t)blockIdx.z * nseg + c / cps) * N * Kd + (int64_t)(i0 + quarter * 32 + lane) * Kd + j0 + half * HALF;
+#pragma unroll
+          for (int q = 0; q < HALF / 4; ++q) {
+            *reinterpret_cast<float4*>(prow + q * 4) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+            acc[4 * q] = 0.f; acc[4 * q + 1] = 0.f; acc[4 * q + 2] = 0.f; acc[4 * q + 3] = 0.f;
+          }
         }
       }
-    }
 #ifdef DGMK_WG_DEBUG
-    wg_prof[6] = nchunks;
+      wg_prof[6] = nchunks;
 #endif
-    if (warp == W_DRAIN) { WG_OUT(24); }
+      if (warp == W_DRAIN) { WG_OUT(24); }
+    } else {
+      // ============================== SEP: MMA issuer (warp 20; 21-23 only hand their registers over) ===
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS_ISSUE_SEP));
+      if (warp == W_ISSUE) {
+#pragma unroll 1
+        for (int64_t c = 0; c < nchunks; ++c) issue(c);
+        WG_OUT(16);
+      }
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
