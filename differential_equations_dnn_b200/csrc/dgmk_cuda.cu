@@ -486,15 +486,15 @@ struct CudaBackend {
       if (!((done_mask >> (dev & 63)) & 1ull)) {
         note(cudaFuncSetAttribute(wg::wgrad_ws_kernel<512, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES));
         note(cudaFuncSetAttribute(wg::wgrad_ws_kernel<128, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES));
-        note(cudaFuncSetAttribute(wg::wgrad_ws_kernel<512, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES));
-        note(cudaFuncSetAttribute(wg::wgrad_ws_kernel<128, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES));
+        note(cudaFuncSetAttribute(wg::wgrad_ws_kernel<512, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES_SEP));
+        note(cudaFuncSetAttribute(wg::wgrad_ws_kernel<128, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES_SEP));
         done_mask |= 1ull << (dev & 63);
       }
       ProfScope ps(PC_WGRAD, st, 2.0 * M * N * Kd, 4.0 * M * (N + Kd + (E ? 4.0 : 0.0)));
       // without the A^T E side product: the variant with its own MMA-issuer warpgroup
       if (!E) {
-        if (lda == 512) wg::wgrad_ws_kernel<512, 128, true><<<gws, wg::NT_SEP, wg::SMEM_BYTES, st>>>(A, S, nullptr, part, nullptr, N, Kd, M, seg_rows, (int)nseg);
-        else wg::wgrad_ws_kernel<128, 128, true><<<gws, wg::NT_SEP, wg::SMEM_BYTES, st>>>(A, S, nullptr, part, nullptr, N, Kd, M, seg_rows, (int)nseg);
+        if (lda == 512) wg::wgrad_ws_kernel<512, 128, true><<<gws, wg::NT_SEP, wg::SMEM_BYTES_SEP, st>>>(A, S, nullptr, part, nullptr, N, Kd, M, seg_rows, (int)nseg);
+        else wg::wgrad_ws_kernel<128, 128, true><<<gws, wg::NT_SEP, wg::SMEM_BYTES_SEP, st>>>(A, S, nullptr, part, nullptr, N, Kd, M, seg_rows, (int)nseg);
       } else if (lda == 512) wg::wgrad_ws_kernel<512, 128, false><<<gws, wg::NT, wg::SMEM_BYTES, st>>>(A, S, E, part, PEw, N, Kd, M, seg_rows, (int)nseg);
       else wg::wgrad_ws_kernel<128, 128, false><<<gws, wg::NT, wg::SMEM_BYTES, st>>>(A, S, E, part, PEw, N, Kd, M, seg_rows, (int)nseg);
       post();

@@ -38,7 +38,11 @@
 //   SEP = true   a sixth warpgroup (warp 20 issues, 21-23 idle) owns the MMAs, so chunk c+1 runs while
 //                chunk c is drained.  No A^T E side product in this variant (its loaders give 8
 //                registers per thread to the new warpgroup): the fused DGM path forms grad[U | b]
-//                elsewhere (input_map_adj) and passes PE = nullptr.
+//                elsewhere (input_map_adj) and passes PE = nullptr.  Warp 21 of that warpgroup feeds the
+//                stagers: cp.async.bulk (TMA engine) of the next raw [32 x 128] S tiles into a 4-deep
+//                shared-memory ring.  With register prefetch the stagers could keep only one chunk
+//                (16 KB per SM) in flight and their period equalled the loaded HBM latency (~1350
+//                cycles per chunk, measured) -- the critical path once the issuer was decoupled.
 // grid = (Kd/128, N/128, splits).
 #pragma once
 #include "dgmk_gemm_tc_tn.cuh"
@@ -72,6 +76,10 @@ constexpr int STAGE_BYTES = 2 * TN_OPER_BYTES;     // hi | lo
 constexpr int BAR_OFF = NB * STAGE_BYTES;
 constexpr int E_OFF = BAR_OFF + 256;               // per loader warp: 32 rows of E (float4)
 constexpr int SMEM_BYTES = E_OFF + 8 * HR * 16 + 1024;   // + alignment slack
+constexpr int RAW_STAGES = 4;                      // SEP: raw S tiles (bulk copies), [32 rows][128] FP32
+constexpr int RAW_BYTES = KC * BN * 4;
+constexpr int RAW_OFF = E_OFF + 8 * HR * 16;
+constexpr int SMEM_BYTES_SEP = RAW_OFF + RAW_STAGES * RAW_BYTES + 1024;
 constexpr int TM_A = 0;                            // 2 buffers x (32 hi | 32 lo)
 constexpr int TM_ACC = 128;                        // 2 buffers x 128
 constexpr int TMEM_COLS = 512;
@@ -87,6 +95,14 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, float v0, float v1, float v2, float v3, float v4, float v5, float v6,
                                          float v7) {
@@ -113,7 +129,7 @@ __global__ void __launch_bounds__(SEP ? NT_SEP : NT, 1) wgrad_ws_kernel(const fl
   char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t bar0 = tctn::smem_u32(smem + BAR_OFF);
   const uint32_t A_FULL = bar0, A_EMPTY = bar0 + 16, B_FULL = bar0 + 32, B_EMPTY = bar0 + 56, T_FULL = bar0 + 80,
-                 T_EMPTY = bar0 + 96;
+                 T_EMPTY = bar0 + 96, RAW_FULL = bar0 + 128, RAW_EMPTY = bar0 + 160;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 112);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -140,6 +156,12 @@ __global__ void __launch_bounds__(SEP ? NT_SEP : NT, 1) wgrad_ws_kernel(const fl
     for (int s = 0; s < NB; ++s) {
       tctn::mbar_init(B_FULL + 8 * s, 4);     // one arrive per stager warp
       tctn::mbar_init(B_EMPTY + 8 * s, 1);    // tcgen05.commit
+    }
+    if (SEP) {
+      for (int s = 0; s < RAW_STAGES; ++s) {
+        tctn::mbar_init(RAW_FULL + 8 * s, 1);    // expect_tx arrive + bytes
+        tctn::mbar_init(RAW_EMPTY + 8 * s, 4);   // one arrive per stager warp
+      }
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -249,6 +271,41 @@ __global__ void __launch_bounds__(SEP ? NT_SEP : NT, 1) wgrad_ws_kernel(const fl
     else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS_STAGE));
     // ================================ S stagers: global -> hi / lo -> shared ring ==============
     const int sw = warp - W_STAGE;                       // rows sw + 4 q of the chunk, columns lane*4 ..
+    if constexpr (SEP) {
+      // raw tiles arrive by bulk copy (warp 21): shared -> registers -> hi / lo operand tile
+      int stage = 0, rs = 0; uint32_t use = 0, ruse = 0;
+      WG_DECL;
+      for (int64_t c = 0; c < nchunks; ++c) {
+        const int64_t m0 = mb + c * KC;
+        WG_T(t0);
+        tctn::mbar_wait(RAW_FULL + 8 * rs, ruse & 1);
+        WG_ADD(0, t0);
+        const char* raw = smem + RAW_OFF + rs * RAW_BYTES + sw * (BN * 4) + lane * 16;
+        float4 v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(raw + q * 4 * (BN * 4));
+        char* sh = smem + stage * STAGE_BYTES;
+        WG_T(t1);
+        tctn::mbar_wait(B_EMPTY + 8 * stage, (use & 1) ^ 1);
+        WG_ADD(1, t1);
+        WG_T(t2);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 x = (m0 + q * 4 + sw < me) ? v[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+          tctn::split_store(sh, sh + TN_OPER_BYTES, tctn::tn_off(q * 4 + sw, lane * 4), x);
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy stores -> UMMA
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(B_FULL + 8 * stage);
+          mbar_arrive(RAW_EMPTY + 8 * rs);     // every lane has its raw values in registers
+        }
+        WG_ADD(2, t2);
+        if (++stage == NB) { stage = 0; ++use; }
+        if (++rs == RAW_STAGES) { rs = 0; ++ruse; }
+      }
+      if (warp == W_STAGE) { WG_OUT(8); }
+    } else {
     const float* sbase = S + j0 + lane * 4;
     float4 va[8], vb[8];
     auto load = [&](float4 (&v)[8], int64_t m0) {
@@ -294,6 +351,7 @@ __global__ void __launch_bounds__(SEP ? NT_SEP : NT, 1) wgrad_ws_kernel(const fl
       }
     }
     if (warp == W_STAGE) { WG_OUT(8); }
+    }
   } else {
     WG_DECL;
     // warp-uniform; one elected lane issues the 12 MMAs of chunk c and the three commits
@@ -378,6 +436,24 @@ __global__ void __launch_bounds__(SEP ? NT_SEP : NT, 1) wgrad_ws_kernel(const fl
 #pragma unroll 1
         for (int64_t c = 0; c < nchunks; ++c) issue(c);
         WG_OUT(16);
+      } else if (warp == W_ISSUE + 1) {
+        // bulk-copy producer: raw S tile of chunk c -> ring stage (rows of S are contiguous when LDS == 128)
+        int rs = 0; uint32_t ruse = 0;
+#pragma unroll 1
+        for (int64_t c = 0; c < nchunks; ++c) {
+          const int64_t m0 = mb + c * KC;
+          const int nrows = (int)((me - m0 < KC) ? me - m0 : KC);
+          tctn::mbar_wait(RAW_EMPTY + 8 * rs, (ruse & 1) ^ 1);
+          const uint32_t dst = tctn::smem_u32(smem + RAW_OFF + rs * RAW_BYTES);
+          if (lane == 0) mbar_expect_tx(RAW_FULL + 8 * rs, (uint32_t)nrows * BN * 4);
+          __syncwarp();
+          if (LDS == BN) {
+            if (lane == 0) bulk_g2s(dst, S + m0 * LDS + j0, (uint32_t)nrows * BN * 4, RAW_FULL + 8 * rs);
+          } else if (lane < nrows) {
+            bulk_g2s(dst + lane * (BN * 4), S + (m0 + lane) * LDS + j0, BN * 4, RAW_FULL + 8 * rs);
+          }
+          if (++rs == RAW_STAGES) { rs = 0; ++ruse; }
+        }
       }
     }
   }

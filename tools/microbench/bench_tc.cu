@@ -88,7 +88,7 @@ int main() {
       float ms = time_ms([&] { dgmk::tctn::gemm_tn_tc_kernel<<<g2, dgmk::tctn::NT, dgmk::tctn::TN_SMEM_BYTES>>>(C, 512, A, 512, E, P, PE, 384, 128, M, rps); }, 10);
       printf("wgrad ZGR [M,384]^T x [M,128] (tc): %.3f ms  %.2f TFLOP/s (fp32-equivalent)\n", ms, 2.0 * M * 384 * 128 / ms * 1e-9);
       CK(cudaFuncSetAttribute(dgmk::wg::wgrad_ws_kernel<512, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dgmk::wg::SMEM_BYTES));
-      CK(cudaFuncSetAttribute(dgmk::wg::wgrad_ws_kernel<512, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dgmk::wg::SMEM_BYTES));
+      CK(cudaFuncSetAttribute(dgmk::wg::wgrad_ws_kernel<512, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dgmk::wg::SMEM_BYTES_SEP));
       for (int sp : {49, 98, 128}) {
         int64_t rps2 = ((M + sp - 1) / sp + 31) / 32 * 32; int splits2 = (int)((M + rps2 - 1) / rps2);
         if (splits2 > splits) continue;
@@ -96,17 +96,17 @@ int main() {
         ms = time_ms([&] { dgmk::wg::wgrad_ws_kernel<512, 512, false><<<g3, dgmk::wg::NT, dgmk::wg::SMEM_BYTES>>>(C, A, E, P, PE, 384, 128, M, rps2, 1); }, 10);
         printf("wgrad ZGR warp-specialised, %d splits: %.3f ms  %.2f TFLOP/s\n", splits2, ms, 2.0 * M * 384 * 128 / ms * 1e-9);
         { long long h[32]; CK(cudaMemcpyFromSymbol(h, dgmk::wg::g_wg_prof, sizeof(h))); double n = (double)h[30];
-          printf("   cycles/chunk (%d chunks): loader[issue_loads %.0f wait_aempty %.0f split+st %.0f E %.0f] stager[issue_loads %.0f wait_bempty %.0f split+sts %.0f] mma[wait_tempty %.0f wait_afull %.0f wait_bfull %.0f issue %.0f] drain[wait_tfull %.0f drain %.0f]\n",
+          printf("   cycles/chunk (%d chunks): loader[issue_loads %.0f wait_aempty %.0f split+st %.0f E %.0f] stager[loads|wait_raw %.0f wait_bempty %.0f split+sts %.0f] mma[wait_tempty %.0f wait_afull %.0f wait_bfull %.0f issue %.0f] drain[wait_tfull %.0f drain %.0f]\n",
                  (int)n, h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[8] / n, h[9] / n, h[10] / n, h[26] / n, h[27] / n, h[28] / n, h[29] / n, h[24] / n, h[25] / n); }
         // the same launch without the A^T E side product (the fused path forms grad[U | b] elsewhere)
-        ms = time_ms([&] { dgmk::wg::wgrad_ws_kernel<512, 512, true><<<g3, dgmk::wg::NT_SEP, dgmk::wg::SMEM_BYTES>>>(C, A, nullptr, P, nullptr, 384, 128, M, rps2, 1); }, 10);
+        ms = time_ms([&] { dgmk::wg::wgrad_ws_kernel<512, 128, true><<<g3, dgmk::wg::NT_SEP, dgmk::wg::SMEM_BYTES_SEP>>>(C, A, nullptr, P, nullptr, 384, 128, M, rps2, 1); }, 10);
         printf("wgrad ZGR warp-specialised, %d splits, no E, separate issuer: %.3f ms  %.2f TFLOP/s\n", splits2, ms, 2.0 * M * 384 * 128 / ms * 1e-9);
         { long long h[32]; CK(cudaMemcpyFromSymbol(h, dgmk::wg::g_wg_prof, sizeof(h))); double n = (double)h[30];
-          printf("   cycles/chunk (%d chunks): loader[issue_loads %.0f wait_aempty %.0f split+st %.0f E %.0f] stager[issue_loads %.0f wait_bempty %.0f split+sts %.0f] mma[wait_tempty %.0f wait_afull %.0f wait_bfull %.0f issue %.0f] drain[wait_tfull %.0f drain %.0f]\n",
+          printf("   cycles/chunk (%d chunks): loader[issue_loads %.0f wait_aempty %.0f split+st %.0f E %.0f] stager[loads|wait_raw %.0f wait_bempty %.0f split+sts %.0f] mma[wait_tempty %.0f wait_afull %.0f wait_bfull %.0f issue %.0f] drain[wait_tfull %.0f drain %.0f]\n",
                  (int)n, h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[8] / n, h[9] / n, h[10] / n, h[18] / n, h[19] / n, h[20] / n, h[21] / n, h[24] / n, h[25] / n); }
         dim3 g4(1, 1, splits2 * 3 > 148 ? 148 : splits2 * 3);
         int64_t rps3 = ((M + g4.z - 1) / g4.z + 31) / 32 * 32;
-        ms = time_ms([&] { dgmk::wg::wgrad_ws_kernel<512, 512, true><<<g4, dgmk::wg::NT_SEP, dgmk::wg::SMEM_BYTES>>>(C, A, nullptr, P, nullptr, 128, 128, M, rps3, 1); }, 10);
+        ms = time_ms([&] { dgmk::wg::wgrad_ws_kernel<512, 128, true><<<g4, dgmk::wg::NT_SEP, dgmk::wg::SMEM_BYTES_SEP>>>(C, A, nullptr, P, nullptr, 128, 128, M, rps3, 1); }, 10);
         printf("wgrad H   warp-specialised, %d splits, no E, separate issuer: %.3f ms  %.2f TFLOP/s\n", g4.z, ms, 2.0 * M * 128 * 128 / ms * 1e-9);
       }
     }
@@ -153,7 +153,7 @@ int main() {
     printf("   g[128*Kd..]= %g %g ref %g %g ; ge[0..1]= %g %g ref %g %g\n", g[128 * Kd], g[128 * Kd + 1], gr[128 * Kd], gr[128 * Kd + 1], ge[0], ge[1], ger[0], ger[1]);
     {
       CK(cudaFuncSetAttribute(dgmk::wg::wgrad_ws_kernel<512, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dgmk::wg::SMEM_BYTES));
-      CK(cudaFuncSetAttribute(dgmk::wg::wgrad_ws_kernel<512, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dgmk::wg::SMEM_BYTES));
+      CK(cudaFuncSetAttribute(dgmk::wg::wgrad_ws_kernel<512, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dgmk::wg::SMEM_BYTES_SEP));
       // two segments of 128 rows per CTA -> 2*splits W partials, 4*splits E partials
       cudaFree(P); CK(cudaMalloc(&P, (size_t)2 * splits * N * Kd * 4));
       float* PE2; CK(cudaMalloc(&PE2, (size_t)4 * splits * 4 * N * 4));
@@ -168,7 +168,7 @@ int main() {
       printf("wgrad_ws   M=%ld N=%d Kd=%d relerr W %.3e  E %.3e\n", (long)M, N, Kd, relerr(g, gr), relerr(ge, ger));
       // the variant with its own MMA-issuer warpgroup (no E)
       CK(cudaMemset(P, 0, (size_t)2 * splits * N * Kd * 4));
-      dgmk::wg::wgrad_ws_kernel<512, 128, true><<<grid, dgmk::wg::NT_SEP, dgmk::wg::SMEM_BYTES>>>(A, S, nullptr, P, nullptr, N, Kd, M, rps / 2, 2);
+      dgmk::wg::wgrad_ws_kernel<512, 128, true><<<grid, dgmk::wg::NT_SEP, dgmk::wg::SMEM_BYTES_SEP>>>(A, S, nullptr, P, nullptr, N, Kd, M, rps / 2, 2);
       CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
       CK(cudaMemcpy(hP.data(), P, hP.size() * 4, cudaMemcpyDeviceToHost));
       for (int n = 0; n < N; ++n) for (int k = 0; k < Kd; ++k) { double s = 0; for (int z = 0; z < 2 * splits; ++z) s += hP[((size_t)z * N + n) * Kd + k]; g[(size_t)n * Kd + k] = (float)s; }
