@@ -104,6 +104,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* src) {
+  asm volatile("prefetch.global.L2 [%0];\n" ::"l"(src) : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, float v0, float v1, float v2, float v3, float v4, float v5, float v6,
                                          float v7) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "f"(v0),
@@ -451,6 +454,15 @@ __global__ void __launch_bounds__(SEP ? NT_SEP : NT, 1) wgrad_ws_kernel(const fl
             if (lane == 0) bulk_g2s(dst, S + m0 * LDS + j0, (uint32_t)nrows * BN * 4, RAW_FULL + 8 * rs);
           } else if (lane < nrows) {
             bulk_g2s(dst + lane * (BN * 4), S + (m0 + lane) * LDS + j0, BN * 4, RAW_FULL + 8 * rs);
+          }
+          // the same chunk of A into L2: this warp runs several chunks ahead of the loaders (ring depth),
+          // whose register prefetch covers only one chunk -- their loads then see L2, not HBM, latency
+          // (prefetch.global.L2 through the LSU, one 128-byte line per lane: cp.async.bulk.prefetch per row cost the
+          // TMA engine more than the copies themselves -- the stagers then waited 1200 cycles per chunk)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int r = q * 8 + (lane >> 2);
+            if (r < nrows) prefetch_l2(A + (m0 + r) * LDA + i0 + (lane & 3) * 32);
           }
           if (++rs == RAW_STAGES) { rs = 0; ++ruse; }
         }
