@@ -24,7 +24,9 @@ struct XSrc {
   int64_t block_stride;  // floats between consecutive blocks when nptr == 1
   int32_t nptr, d;
   DGMK_HD const float* at(int64_t r) const {
-    int64_t b = (nptr == 1 && r < block_rows) ? 0 : ((block_rows >> 31) == 0 ? idiv(r, (int32_t)block_rows) : r / block_rows);
+    // separate arrays: at most three blocks, two comparisons instead of a division
+    int64_t b = (nptr > 1) ? (int64_t)(r >= block_rows) + (int64_t)(r >= 2 * block_rows)
+                           : ((r < block_rows) ? 0 : ((block_rows >> 31) == 0 ? idiv(r, (int32_t)block_rows) : r / block_rows));
     int64_t w = r - b * block_rows;
     // ternaries, not p[b]: a runtime index would spill the parameter array to local memory
     const float* base = (nptr > 1) ? (b == 0 ? p[0] : (b == 1 ? p[1] : p[2])) : p[0] + b * block_stride;
