@@ -7,6 +7,7 @@
 #include "../../differential_equations_dnn_b200/csrc/dgmk_gemm_tc.cuh"
 #include "../../differential_equations_dnn_b200/csrc/dgmk_gemm_tc_tn.cuh"
 #include "../../differential_equations_dnn_b200/csrc/dgmk_wgrad_ws.cuh"
+#include "dgrad_ws_experiment.cuh"
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
 __global__ void naive_nt(const float* A, int64_t lda, const float* Bt, int64_t ldb, float* C, int64_t ldc, int64_t M, int N, int K, bool accum) {
@@ -35,7 +36,7 @@ int main() {
   CK(cudaFuncSetAttribute(gemm_nn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   CK(cudaFuncSetAttribute(gemm_nn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   struct Case { int64_t M; int N, K; bool accum; };
-  Case cases[] = {{128, 128, 32, false}, {128, 128, 128, false}, {1000, 384, 128, false}, {777, 128, 384, true}};
+  Case cases[] = {{128, 128, 32, false}, {128, 128, 128, false}, {1000, 384, 128, false}, {777, 128, 384, true}, {1500, 128, 384, true}, {1000, 128, 128, false}};
   for (auto c : cases) {
     int64_t lda = c.K + 32, ldb = c.K, ldc = c.N + 64;
     std::vector<float> hA(c.M * lda), hB((size_t)c.N * ldb * 3), hC(c.M * ldc);
@@ -60,6 +61,18 @@ int main() {
     CK(cudaMemcpy(r2.data(), Cr, hC.size() * 4, cudaMemcpyDeviceToHost));
     printf("gemm_nn_tc M=%ld N=%d K=%d accum=%d relerr %.3e   C[0..3]= %g %g %g %g  ref %g %g %g %g\n", (long)c.M, c.N, c.K, c.accum,
            relerr(r1, r2), r1[0], r1[1], r1[2], r1[3], r2[0], r2[1], r2[2], r2[3]);
+    // the warp-specialised persistent variant on the same case (few CTAs: every CTA walks several tiles)
+    if (c.N == 128) {
+      CK(cudaFuncSetAttribute(dgmk::dg::dgrad_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dgmk::dg::SMEM_BYTES));
+      CK(cudaFuncSetAttribute(dgmk::dg::dgrad_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dgmk::dg::SMEM_BYTES));
+      CK(cudaMemcpy(C, hC.data(), hC.size() * 4, cudaMemcpyHostToDevice));
+      dim3 g2(3, c.N / BN);
+      if (c.accum) dgmk::dg::dgrad_ws_kernel<true><<<g2, dgmk::dg::NT, dgmk::dg::SMEM_BYTES>>>(A, lda, B, ldb, (int64_t)c.N * ldb, C, ldc, c.M, c.K);
+      else dgmk::dg::dgrad_ws_kernel<false><<<g2, dgmk::dg::NT, dgmk::dg::SMEM_BYTES>>>(A, lda, B, ldb, (int64_t)c.N * ldb, C, ldc, c.M, c.K);
+      CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(r1.data(), C, hC.size() * 4, cudaMemcpyDeviceToHost));
+      printf("dgrad_ws   M=%ld N=%d K=%d accum=%d relerr %.3e\n", (long)c.M, c.N, c.K, c.accum, relerr(r1, r2));
+    }
     cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(Cr);
   }
   {
@@ -77,6 +90,10 @@ int main() {
         else gemm_nn_tc_kernel<false><<<grid, NT, SMEM_BYTES>>>(A, 512, B, t.K, (int64_t)512 * 512, C, 512, M, t.K);
       }, 10);
       printf("%s: %.3f ms  %.2f TFLOP/s (fp32-equivalent)\n", t.name, ms, 2.0 * M * t.N * t.K / ms * 1e-9);
+    }
+    {
+      float ms = time_ms([&] { dgmk::dg::dgrad_ws_kernel<true><<<dim3(148, 1), dgmk::dg::NT, dgmk::dg::SMEM_BYTES>>>(A, 512, B, 384, (int64_t)512 * 512, C, 512, M, 384); }, 10);
+      printf("dgrad ZGR[M,384]x[384,128] warp-specialised persistent: %.3f ms  %.2f TFLOP/s (fp32-equivalent)\n", ms, 2.0 * M * 128 * 384 / ms * 1e-9);
     }
     {
       CK(cudaFuncSetAttribute(dgmk::tctn::gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dgmk::tctn::TN_SMEM_BYTES));
