@@ -29,6 +29,12 @@
 // split weights (3.1 TB/s of L2 -> SM traffic next to 2.6 TB/s for A and C).  The fix is fewer weight
 // bytes per row (weights resident in the shared memory of a 4-CTA cluster that splits K and exchanges
 // partial tiles through distributed shared memory), not a better pipeline -- profiles/r01_notes.md.
+// Per-role cycle counters of this version (cycles per chunk, 2790 in total): A stagers 1490 in split +
+// store (first use of the prefetched registers: latency-bound with one chunk in flight), weight stagers
+// 1370 (same), MMA warp: issue 936, waiting 1580 for operands and accumulators; drain 709 + 968 per
+// chunk for the read-modify-write of C at the end of a tile.  Variants tried on top, all slower:
+// cp.async (LDGSTS) weight staging with deferred publication (0.69-0.80 ms), three register sets for
+// the A stagers, C folded into the accumulators at the start of a tile.
 #pragma once
 #include "../../differential_equations_dnn_b200/csrc/dgmk_gemm_tc_tn.cuh"
 
