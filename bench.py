@@ -236,8 +236,9 @@ def main():
     names = {0: "wg::wgrad_ws_kernel (weight gradient: warp-specialised tcgen05 kind::tf32, A^T in tensor memory, 3xTF32)",
              1: "lg::lane_gemm_kernel (fused GEMM + jet stage: weights in tensor memory, warp-specialised, 3xTF32)",
              2: "tc::gemm_nn_tc_kernel (streaming tcgen05 tile: K = 3H data gradient; FFMA2 tile for H % 128 != 0)",
-             3: "ew_kernel<...> (stand-alone element-wise jet stages, loss, pack, Adam)"}
-    for cls in range(4):
+             3: "ew_kernel<...> / rev1_e_kernel (stand-alone element-wise jet stages, loss, pack, Adam)",
+             4: "wcolsum / rowdot / reduce_partials (output layer, column sums, second-stage reductions)"}
+    for cls in range(5):
         t_, n_, f_, b_ = C.c_double(), C.c_longlong(), C.c_double(), C.c_double()
         _cabi.check(lib.dgmk_profile_read(cls, C.byref(t_), C.byref(n_), C.byref(f_), C.byref(b_)))
         per_step = (W + a.steps)   # the profile spans warm-up + timed steps: identical work per step
