@@ -167,6 +167,11 @@ def main():
 
     lib = _cabi.load()  # raises if the CUDA library is missing: no fallback
     assert torch.cuda.is_available(), "bench.py (b200 arm) needs a GPU"
+    # stdout carries exactly one JSON line: keep NCCL's own banner ("NCCL version ...", printed to stdout
+    # when a box exports NCCL_DEBUG=VERSION) out of it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     parallel.init_from_env("nccl")
     if dist.is_initialized():
         parallel.enable_data_parallel()
