@@ -8,6 +8,7 @@ import torch
 from . import autograd as ag
 from . import parallel
 from ._flat import deferred_forward
+from ._loop import graphed_loop, print_progress
 from .auxiliary_funs import fn_timer
 from .heat import _device
 from .optim import FusedAdam
@@ -39,22 +40,40 @@ def dgm_loss_func(y, y0, t, y_ic):
 
 
 @fn_timer
-def minimize_loss_dgm(net, y_ic, iterations=1000, batch_size=32, lrate=1e-4, sampler="grid"):
+def minimize_loss_dgm(net, y_ic, iterations=1000, batch_size=32, lrate=1e-4, sampler="grid", cuda_graph=False):
     """fitzhugh_nagumo.py:100-156.  sampler="grid" is the shipped one: `batch_size` (<=200)
     distinct nodes of a 200-point grid on [0,30] (:123-133); sampler="uniform" is the
-    commented-out `30.01 * rand` (:129), the only one that scales past 200 rows."""
+    commented-out `30.01 * rand` (:129), the only one that scales past 200 rows.
+    `cuda_graph=True` (single GPU): one captured iteration replayed (`_loop.graphed_loop`)."""
     device = _device()
-    optimizer = FusedAdam(net.parameters(), lr=lrate)
+    graphed = cuda_graph and not parallel.is_enabled()
+    optimizer = FusedAdam(net.parameters(), lr=lrate, capturable=graphed)
     t0 = torch.zeros([batch_size, 1], device=device)
     num_samples = 200
     T = torch.linspace(0.0, 30.0, steps=num_samples, device=device)
     prob = torch.full((num_samples,), 1.0 / num_samples, device=device)
+
+    def sample():
+        if sampler == "grid":
+            return T[prob.multinomial(num_samples=batch_size, replacement=False)].reshape(-1, 1)
+        return 30.01 * torch.rand([batch_size, 1], device=device)
+
+    if graphed:
+        def step():
+            t = sample()
+            optimizer.zero_grad()
+            with deferred_forward(net):
+                y, y0 = net(t), net(t0)
+            loss = dgm_loss_func(y, y0, t, y_ic)
+            loss.backward()
+            optimizer.step()
+            return loss
+        train_loss = graphed_loop(step, iterations, device)
+        print_progress(train_loss, lrate, parallel.rank())
+        return net, train_loss
     losses = []
     for i in range(iterations):
-        if sampler == "grid":
-            t = T[prob.multinomial(num_samples=batch_size, replacement=False)].reshape(-1, 1)
-        else:
-            t = 30.01 * torch.rand([batch_size, 1], device=device)
+        t = sample()
         optimizer.zero_grad()
         with deferred_forward(net):
             y, y0 = net(t), net(t0)

@@ -9,6 +9,7 @@ import torch
 from . import autograd as ag
 from . import parallel
 from ._flat import FlatParamModule
+from ._loop import graphed_loop, print_progress
 from .auxiliary_funs import fn_timer
 from .heat import _device
 from .optim import FusedAdam
@@ -41,10 +42,23 @@ def dgm_loss_func(net, x, k=50, nodes=None):
 
 
 @fn_timer
-def minimize_loss_dgm(net, y_ic=2.0, iterations=1000, batch_size=32, lrate=1e-4, k=50):
-    """fredholm.py:77-117 (y_ic is accepted and unused, as there)."""
+def minimize_loss_dgm(net, y_ic=2.0, iterations=1000, batch_size=32, lrate=1e-4, k=50, cuda_graph=False):
+    """fredholm.py:77-117 (y_ic is accepted and unused, as there).
+    `cuda_graph=True` (single GPU): one captured iteration replayed (`_loop.graphed_loop`)."""
     device = _device()
-    optimizer = FusedAdam(net.parameters(), lr=lrate)
+    graphed = cuda_graph and not parallel.is_enabled()
+    optimizer = FusedAdam(net.parameters(), lr=lrate, capturable=graphed)
+    if graphed:
+        def step():
+            t = np.pi / 2.0 * torch.rand([batch_size, 1], device=device)
+            optimizer.zero_grad()
+            loss = dgm_loss_func(net, t, k)
+            loss.backward()
+            optimizer.step()
+            return loss
+        train_loss = graphed_loop(step, iterations, device)
+        print_progress(train_loss, lrate, parallel.rank())
+        return net, train_loss
     losses = []
     for i in range(iterations):
         t = np.pi / 2.0 * torch.rand([batch_size, 1], device=device)

@@ -11,6 +11,7 @@ import torch
 from . import autograd as ag
 from . import parallel
 from ._flat import DeferredOutput, FlatParamModule, deferred_forward  # noqa: F401
+from ._loop import graphed_loop, print_progress
 from .auxiliary_funs import fn_timer
 from .optim import FusedAdam
 
@@ -52,22 +53,16 @@ def reference_style_loss(net, x, x0, xbd1, xbd2, x_bd1, x_bd2, kappa=1.0):
 
 
 def _minimize_graphed(net, iterations, batch_size, lrate, warmup=11):
-    """The same training loop with one iteration (device-side sampler, fused loss + gradient, fused
-    Adam with a device-resident step counter, loss record) captured in a CUDA graph and replayed:
-    at the reference's batch sizes (32-256 rows) the step is launch-bound, and a replay costs one
-    graph launch instead of ~150 kernel launches plus the Python between them.
-    The first `warmup` iterations run eagerly (they also size the caches the capture relies on).
-    Same RNG stream, same arithmetic as the eager loop."""
+    """The training loop with one captured iteration replayed (`_loop.graphed_loop`): same RNG stream,
+    same arithmetic as the eager loop."""
     device = _device()
     optimizer = FusedAdam(net.parameters(), lr=lrate, capturable=True)
     t0 = torch.zeros([batch_size, 1], device=device)
     xbd1 = torch.zeros([batch_size, 1], device=device)
     xbd2x = torch.ones([batch_size, 1], device=device) * torch.pi
     xbd2y = torch.zeros([batch_size, 1], device=device)
-    losses = torch.zeros(max(iterations, 1), device=device)
-    idx = torch.zeros(1, dtype=torch.int64, device=device)
 
-    def one_iteration():
+    def step():
         x = torch.pi * torch.rand([batch_size, 1], device=device)
         t = 3.0 * torch.rand([batch_size, 1], device=device)
         X = torch.cat([x, t], dim=1)
@@ -78,27 +73,10 @@ def _minimize_graphed(net, iterations, batch_size, lrate, warmup=11):
         loss = dgm_loss_func(net, X, X0, X_BD1, X_BD2, xbd1, xbd2y)
         loss.backward()
         optimizer.step()
-        losses.index_copy_(0, idx, loss.detach().reshape(1))
-        idx.add_(1)
+        return loss
 
-    n_eager = min(warmup, iterations)
-    side = torch.cuda.Stream(device=device)
-    side.wait_stream(torch.cuda.current_stream(device))
-    with torch.cuda.stream(side):          # warm-up on the stream family the capture will use
-        for _ in range(n_eager):
-            one_iteration()
-    torch.cuda.current_stream(device).wait_stream(side)
-    if iterations > n_eager:
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side):
-            one_iteration()
-        # the capture itself does not execute: iteration n_eager is the first replay
-        for _ in range(iterations - n_eager):
-            graph.replay()
-    train_loss = losses[:iterations].cpu().tolist()
-    if parallel.rank() == 0:
-        for i in range(0, iterations, 100):
-            print(f"Iteration: {i}, Loss: {train_loss[i]}, LR: {lrate}")
+    train_loss = graphed_loop(step, iterations, device, warmup)
+    print_progress(train_loss, lrate, parallel.rank())
     return net, train_loss
 
 

@@ -9,6 +9,7 @@ import torch
 from . import autograd as ag
 from . import parallel
 from ._flat import DeferredOutput, deferred_forward
+from ._loop import graphed_loop, print_progress
 from .auxiliary_funs import fn_timer
 from .heat import _device
 from .optim import FusedAdam
@@ -46,12 +47,27 @@ def dgm_loss_func(y, y0, t, y_ic):
 
 
 @fn_timer
-def minimize_loss_dgm(net, y_ic=2.0, iterations=1000, batch_size=32, lrate=1e-4):
-    """simple_ode.py:66-112: t ~ 1.01 U[0,1), Adam(lr); returns (net, list[float])."""
+def minimize_loss_dgm(net, y_ic=2.0, iterations=1000, batch_size=32, lrate=1e-4, cuda_graph=False):
+    """simple_ode.py:66-112: t ~ 1.01 U[0,1), Adam(lr); returns (net, list[float]).
+    `cuda_graph=True` (single GPU): one captured iteration replayed (`_loop.graphed_loop`)."""
     device = _device()
-    optimizer = FusedAdam(net.parameters(), lr=lrate)
+    graphed = cuda_graph and not parallel.is_enabled()
+    optimizer = FusedAdam(net.parameters(), lr=lrate, capturable=graphed)
     y_ic = torch.ones([batch_size, 1], device=device) * y_ic
     t0 = torch.zeros([batch_size, 1], device=device)
+    if graphed:
+        def step():
+            t = 1.01 * torch.rand([batch_size, 1], device=device)
+            optimizer.zero_grad()
+            with deferred_forward(net):
+                y, y0 = net(t), net(t0)
+            loss = dgm_loss_func(y, y0, t, y_ic)
+            loss.backward()
+            optimizer.step()
+            return loss
+        train_loss = graphed_loop(step, iterations, device)
+        print_progress(train_loss, lrate, parallel.rank())
+        return net, train_loss
     losses = []
     for i in range(iterations):
         t = 1.01 * torch.rand([batch_size, 1], device=device)

@@ -232,6 +232,40 @@ def test_cuda_graph_driver_matches_eager():
     assert graphed[-1] < graphed[0]
 
 
+@pytest.mark.parametrize("problem", ["simple_ode", "fhn_uniform", "fredholm"])
+def test_cuda_graph_driver_other_problems(problem):
+    """The same replay driver behind the other three `minimize_loss_dgm` (simple_ode.py:66-112,
+    fitzhugh_nagumo.py:100-156 with the uniform sampler, fredholm.py:77-117): the graphed loop follows
+    the eager one (same RNG stream and arithmetic)."""
+    from differential_equations_dnn_b200 import neural_networks, simple_ode, fitzhugh_nagumo, fredholm
+    its = 40
+    curves = []
+    for graph in (False, True):
+        torch.manual_seed(1234)
+        if problem == "simple_ode":
+            net = neural_networks.MLP(input_dim=1, output_dim=1, hidden_size=32).cuda()
+        elif problem == "fhn_uniform":
+            net = neural_networks.MLP(input_dim=1, output_dim=2, hidden_size=32, num_layers=2, activation="tanh").cuda()
+        else:
+            net = neural_networks.DGM(input_dim=1, output_dim=1, hidden_size=32).cuda()
+        torch.manual_seed(7)
+        torch.cuda.manual_seed(7)
+        if problem == "simple_ode":
+            _, loss = simple_ode.minimize_loss_dgm(net, y_ic=2.0, iterations=its, batch_size=64, lrate=1e-3, cuda_graph=graph)
+        elif problem == "fhn_uniform":
+            y_ic = torch.zeros([64, 2], device="cuda")
+            _, loss = fitzhugh_nagumo.minimize_loss_dgm(net, y_ic, iterations=its, batch_size=64, lrate=1e-3,
+                                                        sampler="uniform", cuda_graph=graph)
+        else:
+            _, loss = fredholm.minimize_loss_dgm(net, iterations=its, batch_size=32, lrate=1e-3, k=8, cuda_graph=graph)
+        assert len(loss) == its and np.all(np.isfinite(loss))
+        assert torch.isfinite(net.flat_theta()).all()
+        curves.append(np.array(loss))
+    eager, graphed = curves
+    assert np.allclose(eager[:15], graphed[:15], rtol=1e-4), (eager[:15], graphed[:15])
+    assert abs(eager[-10:].mean() - graphed[-10:].mean()) <= 0.25 * abs(eager[-10:].mean()) + 1e-6
+
+
 @pytest.mark.parametrize("kind", ["dgm", "mlp"])
 def test_eval_and_jets_hidden128(kind):
     """Hidden size 128 through the module seams: value-only evaluation (fused forward kernels, ragged
