@@ -38,7 +38,6 @@ def main():
         t_, n_, f_, b_ = C.c_double(), C.c_longlong(), C.c_double(), C.c_double()
         if lib.dgmk_profile_read(c, C.byref(t_), C.byref(n_), C.byref(f_), C.byref(b_)) == 0:
             cls.append(f"{c}:{t_.value / 2:.2f}ms/{n_.value // 2}")
-    g = out[0] if isinstance(out, (tuple, list)) else out
     print(f"{tag} {ms:.2f} ms/step {B / ms * 1e3:.3e} rows/s | " + " ".join(cls) + f" | loss {out[-1].item():.6f}", flush=True)
 
 
