@@ -192,7 +192,8 @@ def test_vs_oracle_midsize(K):
         assert rel(out[off:off + n], g_ref.numpy()[off:off + n]) < TOL
 
 
-@pytest.mark.parametrize("kind,prob", [("dgm", "heat"), ("mlp", "heat"), ("dgm", "fhn"), ("mlp", "ode128")])
+@pytest.mark.parametrize("kind,prob", [("dgm", "heat"), ("mlp", "heat"), ("dgm", "fhn"), ("mlp", "ode128"),
+                                       ("dgmraw", "heat"), ("dgmraw", "fredholm")])
 def test_engines_agree(K, kind, prob):
     """The fused units-on-lanes kernels + warp-specialised weight gradient (engine 1), the streaming
     tcgen05 tiles + separate element-wise kernels (engine 2) and the FP32 FFMA2 tiles (engine 0)
@@ -204,8 +205,20 @@ def test_engines_agree(K, kind, prob):
     torch.manual_seed(7)
     B = 3000 + 37
     gen = torch.Generator().manual_seed(11)
-    if prob == "heat":
-        net = (dgm_net.DGM(2, 1, 128, 2) if kind == "dgm" else neural_networks.MLP(2, 1, 128, 2, activation="tanh")).cuda()
+    if prob == "fredholm":   # neural_networks.DGM (raw [in,out] parameters, ReLU gates) on the value-only channel set
+        net = neural_networks.DGM(1, 1, 128, 2).cuda()
+        with torch.no_grad():   # biases start at zero there (neural_networks.py:93-96): move off the ReLU ties
+            net.flat_theta().add_(0.01 * torch.randn(net.flat_theta().shape, generator=gen).cuda())
+        B = 500 + 13
+        host = [(np.pi / 2) * torch.rand([B, 1], generator=gen), (np.pi / 2) * torch.rand([6, B, 1], generator=gen)]
+        fn, ofn = K.fredholm_step, jets_np.fredholm_step
+    elif prob == "heat":
+        if kind == "dgmraw":
+            net = neural_networks.DGM(2, 1, 128, 2).cuda()
+            with torch.no_grad():
+                net.flat_theta().add_(0.01 * torch.randn(net.flat_theta().shape, generator=gen).cuda())
+        else:
+            net = (dgm_net.DGM(2, 1, 128, 2) if kind == "dgm" else neural_networks.MLP(2, 1, 128, 2, activation="tanh")).cuda()
         x = torch.pi * torch.rand([B, 1], generator=gen); t = 3.0 * torch.rand([B, 1], generator=gen); z = torch.zeros(B, 1)
         host = [torch.cat([x, t], 1), torch.cat([x, z], 1), torch.cat([z, t], 1), torch.cat([z + torch.pi, t], 1), z, z.clone()]
         fn, ofn = K.heat_step, jets_np.heat_step
@@ -228,8 +241,12 @@ def test_engines_agree(K, kind, prob):
             out[eng] = fn(d, net.flat_theta(), *args).double().cpu().numpy()
     finally:
         lib.dgmk_set_gemm_engine(1)
+    # ReLU gates (neural_networks.DGM): a pre-activation within FP32 rounding of 0 lands on the other side of
+    # the kink than in FP64 and flips that row's derivative -- the FP32 reference itself is only within a few
+    # 1e-5 of FP64 there, every engine alike
+    tol = 1e-4 if kind == "dgmraw" else TOL
     for eng in (0, 2, 1):
-        assert abs(out[eng][-1] - lo) <= TOL * abs(lo), (eng, out[eng][-1], lo)
+        assert abs(out[eng][-1] - lo) <= tol * abs(lo), (eng, out[eng][-1], lo)
         for (_, off, n, live) in net.param_slices():
             if live and np.linalg.norm(go[off:off + n]) > 0:
-                assert rel(out[eng][off:off + n], go[off:off + n]) < TOL, (eng, off, rel(out[eng][off:off + n], go[off:off + n]))
+                assert rel(out[eng][off:off + n], go[off:off + n]) < tol, (eng, off, rel(out[eng][off:off + n], go[off:off + n]))
