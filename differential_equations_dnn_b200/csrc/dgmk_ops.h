@@ -352,6 +352,67 @@ struct DgmRev1Fn {
 #pragma unroll
     for (int c = 0; c < CS::C; ++c) SBp[sb + (int64_t)c * Hp] = yb[c];
   }
+  // the same arithmetic on values already in registers (run4 below)
+  DGMK_HD static void core(const float* afz, const float* afg, const float* afh, const float* s, const float* nb,
+                           float* abz, float* abg, float* abh, float* sbp) {
+    float z[CS::C], omg[CS::C], h[CS::C], yb[CS::C];
+    aform_to_jet<CS, ACT>(afz, z);
+    aform_to_jet<CS, ACT>(afg, omg);
+    aform_to_jet<CS, ACT>(afh, h);
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) omg[c] = -omg[c];
+    omg[0] += 1.0f;
+    prod_adj<CS, false>(nb, omg, yb);  // Hbar
+    act_adj<CS, ACT>(yb, afh, abh);
+    prod_adj<CS, false>(nb, h, yb);    // -(Gbar)
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) yb[c] = -yb[c];
+    act_adj<CS, ACT>(yb, afg, abg);
+    prod_adj<CS, false>(nb, s, yb);    // Zbar
+    act_adj<CS, ACT>(yb, afz, abz);
+    prod_adj<CS, false>(nb, z, sbp);   // direct path to s
+  }
+  // four consecutive units of one point (Hp % 4 == 0): 16-byte accesses, the index division once per four
+  // elements; k = p * (Hp/4) + j/4.  sink(u, slot, ab) as in run(), u = unit within the quad
+  template <class Sink>
+  DGMK_HD void run4(int64_t k, Sink&& sink) const {
+    const int q = Hp >> 2;
+    int64_t p = idiv(k, q); int j = (int)(k - p * q) * 4;
+    const int64_t ld = 4 * (int64_t)Hp;
+    const float* row = A4 + (p * CS::C) * ld + j;
+    float* orow = AB4 + (p * CS::C) * ld + j;
+    const int64_t sb = (p * CS::C) * Hp + j;
+    F4 vz[CS::C], vg[CS::C], vh[CS::C], vs[CS::C], vn[CS::C];
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) {
+      vz[c] = *reinterpret_cast<const F4*>(row + c * ld); vg[c] = *reinterpret_cast<const F4*>(row + c * ld + Hp);
+      vh[c] = *reinterpret_cast<const F4*>(row + c * ld + 3 * Hp);
+      vs[c] = *reinterpret_cast<const F4*>(S + sb + (int64_t)c * Hp); vn[c] = *reinterpret_cast<const F4*>(SBn + sb + (int64_t)c * Hp);
+    }
+    float oz[4][CS::C], og[4][CS::C], oh[4][CS::C], os[4][CS::C];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float afz[CS::C], afg[CS::C], afh[CS::C], s[CS::C], nb[CS::C];
+#pragma unroll
+      for (int c = 0; c < CS::C; ++c) {
+        afz[c] = u == 0 ? vz[c].x : (u == 1 ? vz[c].y : (u == 2 ? vz[c].z : vz[c].w));
+        afg[c] = u == 0 ? vg[c].x : (u == 1 ? vg[c].y : (u == 2 ? vg[c].z : vg[c].w));
+        afh[c] = u == 0 ? vh[c].x : (u == 1 ? vh[c].y : (u == 2 ? vh[c].z : vh[c].w));
+        s[c] = u == 0 ? vs[c].x : (u == 1 ? vs[c].y : (u == 2 ? vs[c].z : vs[c].w));
+        nb[c] = u == 0 ? vn[c].x : (u == 1 ? vn[c].y : (u == 2 ? vn[c].z : vn[c].w));
+      }
+      core(afz, afg, afh, s, nb, oz[u], og[u], oh[u], os[u]);
+      sink(u, 3, oh[u]); sink(u, 1, og[u]); sink(u, 0, oz[u]);
+    }
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) {
+      F4 v;
+      v.x = oh[0][c]; v.y = oh[1][c]; v.z = oh[2][c]; v.w = oh[3][c]; *reinterpret_cast<F4*>(orow + c * ld + 3 * Hp) = v;
+      v.x = og[0][c]; v.y = og[1][c]; v.z = og[2][c]; v.w = og[3][c]; *reinterpret_cast<F4*>(orow + c * ld + Hp) = v;
+      v.x = oz[0][c]; v.y = oz[1][c]; v.z = oz[2][c]; v.w = oz[3][c]; *reinterpret_cast<F4*>(orow + c * ld) = v;
+      v.x = os[0][c]; v.y = os[1][c]; v.z = os[2][c]; v.w = os[3][c]; *reinterpret_cast<F4*>(SBp + sb + (int64_t)c * Hp) = v;
+    }
+  }
 };
 // reverse stage 2: (s*R)bar -> abar_R (slot 2), s bar += R * (sR)bar
 template <class CS, int ACT>
