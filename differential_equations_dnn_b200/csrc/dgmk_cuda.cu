@@ -18,6 +18,9 @@ constexpr int EW_THREADS = 256;
 #ifndef REV1_MINB_V
 #define REV1_MINB_V 6
 #endif
+#ifndef REV1_V_HEAT
+#define REV1_V_HEAT 2
+#endif
 
 // number of kernels this library has launched in this process (diagnostic: bench.py
 // reports it as gpu_launches)
@@ -138,45 +141,46 @@ __global__ void __launch_bounds__(EW_THREADS, MINB) rev1_e_kernel(const F f, con
   }
 }
 
-// Four units per thread (value-only channel set: 16-byte accesses; the scalar version of this light stage
-// ran at 0.74 of the measured HBM peak).  Thread = unit quad q = tid % 32 for its whole life; eight threads
-// of a block share a quad.  Same part layout as rev1_e_kernel.
-template <class CS>
-struct Rev1Sink4 {
+// V units per thread (8- / 16-byte accesses): the scalar version of the value-only stage ran at 0.74 of the
+// measured HBM peak, four units per thread took 2.7 ms off the step.  Thread = unit group q = tid % (128 / V)
+// for its whole life; 2 V threads of a block share a group.  Same part layout as rev1_e_kernel.
+template <class CS, int V>
+struct Rev1SinkV {
   float x0, x1; float (*g)[3][3];
   __device__ __forceinline__ void operator()(int u, int slot, const float* ab) const { input_map_adj<CS>(ab, x0, x1, g[u][slot == 3 ? 2 : slot]); }
 };
-template <class F, class CS>
-__global__ void __launch_bounds__(EW_THREADS, 3) rev1_e4_kernel(const F f, const XSrc xs, int64_t n4, float* __restrict__ part) {
-  float g[4][3][3];
+template <class F, class CS, int V, int MINB>
+__global__ void __launch_bounds__(EW_THREADS, MINB) rev1_ev_kernel(const F f, const XSrc xs, int64_t nv, float* __restrict__ part) {
+  constexpr int GROUPS = 128 / V;
+  float g[V][3][3];
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+  for (int u = 0; u < V; ++u)
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
       for (int e = 0; e < 3; ++e) g[u][a][e] = 0.f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += stride) {
-    const float* x = xs.at(k >> 5);
-    Rev1Sink4<CS> sink;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nv; k += stride) {
+    const float* x = xs.at(k / GROUPS);
+    Rev1SinkV<CS, V> sink;
     sink.x0 = __ldg(x); sink.x1 = (xs.d > 1) ? __ldg(x + 1) : 0.f; sink.g = g;
-    f.run4(k, sink);
+    f.template runv<V>(k, sink);
   }
-  __shared__ float sm[36][EW_THREADS];
+  __shared__ float sm[V * 9][EW_THREADS];
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+  for (int u = 0; u < V; ++u)
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
       for (int e = 0; e < 3; ++e) sm[u * 9 + a * 3 + e][threadIdx.x] = g[u][a][e];
   __syncthreads();
   if (threadIdx.x < 128) {
-    const int q = threadIdx.x >> 2, u = threadIdx.x & 3;
+    const int q = threadIdx.x / V, u = threadIdx.x % V;
 #pragma unroll
     for (int ge = 0; ge < 9; ++ge) {
       float s = 0.f;
 #pragma unroll
-      for (int r = 0; r < EW_THREADS / 32; ++r) s += sm[u * 9 + ge][q + 32 * r];
+      for (int r = 0; r < EW_THREADS / GROUPS; ++r) s += sm[u * 9 + ge][q + GROUPS * r];
       part[((int64_t)blockIdx.x * 9 + ge) * 128 + threadIdx.x] = s;
     }
   }
@@ -448,15 +452,18 @@ struct CudaBackend {
     if (cap > part_n / (9 * 128)) cap = part_n / (9 * 128);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) { if (!err) err = "internal: partial buffer too small"; return; }
-    if constexpr (CS::C == 1) {   // value-only rows: four units per thread
-      const int64_t n4 = rows * 32;
-      int64_t b4 = (n4 + EW_THREADS - 1) / EW_THREADS;
-      int64_t cap4 = (int64_t)sms * 3;
-      if (cap4 > part_n / (9 * 128)) cap4 = part_n / (9 * 128);
-      if (b4 > cap4) b4 = cap4;
-      blocks = b4;
+    // units per thread: 4 (value-only rows), 2 (heat: four channels per unit), 1 otherwise
+    constexpr int V = (CS::C == 1) ? 4 : (CS::C == 4 ? REV1_V_HEAT : 1);
+    if constexpr (V > 1) {
+      constexpr int MB = (CS::C == 1) ? 3 : 2;
+      const int64_t nv = rows * (128 / V);
+      int64_t bv = (nv + EW_THREADS - 1) / EW_THREADS;
+      int64_t capv = (int64_t)sms * MB;
+      if (capv > part_n / (9 * 128)) capv = part_n / (9 * 128);
+      if (bv > capv) bv = capv;
+      blocks = bv;
       ProfScope ps(PC_EW, st, 0.0, 0.0);
-      rev1_e4_kernel<F, CS><<<(unsigned)blocks, EW_THREADS, 0, st>>>(f, xs, n4, part);
+      rev1_ev_kernel<F, CS, V, MB><<<(unsigned)blocks, EW_THREADS, 0, st>>>(f, xs, nv, part);
       post();
     } else {
       ProfScope ps(PC_EW, st, 0.0, 0.0);

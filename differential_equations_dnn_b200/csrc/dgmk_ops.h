@@ -372,45 +372,41 @@ struct DgmRev1Fn {
     act_adj<CS, ACT>(yb, afz, abz);
     prod_adj<CS, false>(nb, z, sbp);   // direct path to s
   }
-  // four consecutive units of one point (Hp % 4 == 0): 16-byte accesses, the index division once per four
-  // elements; k = p * (Hp/4) + j/4.  sink(u, slot, ab) as in run(), u = unit within the quad
-  template <class Sink>
-  DGMK_HD void run4(int64_t k, Sink&& sink) const {
-    const int q = Hp >> 2;
-    int64_t p = idiv(k, q); int j = (int)(k - p * q) * 4;
+  // V = 2 or 4 consecutive units of one point (Hp % V == 0): 8- / 16-byte accesses, the index division once
+  // per V elements; k = p * (Hp/V) + j/V.  sink(u, slot, ab) as in run(), u = unit within the group
+  template <int V> struct alignas(4 * V) Vec { float v[V]; };
+  template <int V, class Sink>
+  DGMK_HD void runv(int64_t k, Sink&& sink) const {
+    const int q = Hp / V;
+    int64_t p = idiv(k, q); int j = (int)(k - p * q) * V;
     const int64_t ld = 4 * (int64_t)Hp;
     const float* row = A4 + (p * CS::C) * ld + j;
     float* orow = AB4 + (p * CS::C) * ld + j;
     const int64_t sb = (p * CS::C) * Hp + j;
-    F4 vz[CS::C], vg[CS::C], vh[CS::C], vs[CS::C], vn[CS::C];
+    Vec<V> vz[CS::C], vg[CS::C], vh[CS::C], vs[CS::C], vn[CS::C];
 #pragma unroll
     for (int c = 0; c < CS::C; ++c) {
-      vz[c] = *reinterpret_cast<const F4*>(row + c * ld); vg[c] = *reinterpret_cast<const F4*>(row + c * ld + Hp);
-      vh[c] = *reinterpret_cast<const F4*>(row + c * ld + 3 * Hp);
-      vs[c] = *reinterpret_cast<const F4*>(S + sb + (int64_t)c * Hp); vn[c] = *reinterpret_cast<const F4*>(SBn + sb + (int64_t)c * Hp);
+      vz[c] = *reinterpret_cast<const Vec<V>*>(row + c * ld); vg[c] = *reinterpret_cast<const Vec<V>*>(row + c * ld + Hp);
+      vh[c] = *reinterpret_cast<const Vec<V>*>(row + c * ld + 3 * Hp);
+      vs[c] = *reinterpret_cast<const Vec<V>*>(S + sb + (int64_t)c * Hp); vn[c] = *reinterpret_cast<const Vec<V>*>(SBn + sb + (int64_t)c * Hp);
     }
-    float oz[4][CS::C], og[4][CS::C], oh[4][CS::C], os[4][CS::C];
+    Vec<V> oz[CS::C], og[CS::C], oh[CS::C], os[CS::C];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float afz[CS::C], afg[CS::C], afh[CS::C], s[CS::C], nb[CS::C];
+    for (int u = 0; u < V; ++u) {
+      float afz[CS::C], afg[CS::C], afh[CS::C], s[CS::C], nb[CS::C], abz[CS::C], abg[CS::C], abh[CS::C], sbp[CS::C];
 #pragma unroll
-      for (int c = 0; c < CS::C; ++c) {
-        afz[c] = u == 0 ? vz[c].x : (u == 1 ? vz[c].y : (u == 2 ? vz[c].z : vz[c].w));
-        afg[c] = u == 0 ? vg[c].x : (u == 1 ? vg[c].y : (u == 2 ? vg[c].z : vg[c].w));
-        afh[c] = u == 0 ? vh[c].x : (u == 1 ? vh[c].y : (u == 2 ? vh[c].z : vh[c].w));
-        s[c] = u == 0 ? vs[c].x : (u == 1 ? vs[c].y : (u == 2 ? vs[c].z : vs[c].w));
-        nb[c] = u == 0 ? vn[c].x : (u == 1 ? vn[c].y : (u == 2 ? vn[c].z : vn[c].w));
-      }
-      core(afz, afg, afh, s, nb, oz[u], og[u], oh[u], os[u]);
-      sink(u, 3, oh[u]); sink(u, 1, og[u]); sink(u, 0, oz[u]);
+      for (int c = 0; c < CS::C; ++c) { afz[c] = vz[c].v[u]; afg[c] = vg[c].v[u]; afh[c] = vh[c].v[u]; s[c] = vs[c].v[u]; nb[c] = vn[c].v[u]; }
+      core(afz, afg, afh, s, nb, abz, abg, abh, sbp);
+      sink(u, 3, abh); sink(u, 1, abg); sink(u, 0, abz);
+#pragma unroll
+      for (int c = 0; c < CS::C; ++c) { oz[c].v[u] = abz[c]; og[c].v[u] = abg[c]; oh[c].v[u] = abh[c]; os[c].v[u] = sbp[c]; }
     }
 #pragma unroll
     for (int c = 0; c < CS::C; ++c) {
-      F4 v;
-      v.x = oh[0][c]; v.y = oh[1][c]; v.z = oh[2][c]; v.w = oh[3][c]; *reinterpret_cast<F4*>(orow + c * ld + 3 * Hp) = v;
-      v.x = og[0][c]; v.y = og[1][c]; v.z = og[2][c]; v.w = og[3][c]; *reinterpret_cast<F4*>(orow + c * ld + Hp) = v;
-      v.x = oz[0][c]; v.y = oz[1][c]; v.z = oz[2][c]; v.w = oz[3][c]; *reinterpret_cast<F4*>(orow + c * ld) = v;
-      v.x = os[0][c]; v.y = os[1][c]; v.z = os[2][c]; v.w = os[3][c]; *reinterpret_cast<F4*>(SBp + sb + (int64_t)c * Hp) = v;
+      *reinterpret_cast<Vec<V>*>(orow + c * ld + 3 * Hp) = oh[c];
+      *reinterpret_cast<Vec<V>*>(orow + c * ld + Hp) = og[c];
+      *reinterpret_cast<Vec<V>*>(orow + c * ld) = oz[c];
+      *reinterpret_cast<Vec<V>*>(SBp + sb + (int64_t)c * Hp) = os[c];
     }
   }
 };
