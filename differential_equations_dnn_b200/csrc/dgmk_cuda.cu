@@ -452,8 +452,8 @@ struct CudaBackend {
     if (cap > part_n / (9 * 128)) cap = part_n / (9 * 128);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) { if (!err) err = "internal: partial buffer too small"; return; }
-    // units per thread: 4 (value-only rows), 2 (heat: four channels per unit), 1 otherwise
-    constexpr int V = (CS::C == 1) ? 4 : (CS::C == 4 ? REV1_V_HEAT : 1);
+    // units per thread: 4 (value-only and ODE / FHN rows), 2 (heat: four channels per unit)
+    constexpr int V = (CS::C <= 2) ? 4 : (CS::C == 4 ? REV1_V_HEAT : 1);
     if constexpr (V > 1) {
       constexpr int MB = (CS::C == 1) ? 3 : 2;
       const int64_t nv = rows * (128 / V);
