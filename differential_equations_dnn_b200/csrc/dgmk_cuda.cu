@@ -15,12 +15,6 @@
 namespace dgmk {
 
 constexpr int EW_THREADS = 256;
-#ifndef REV1_MINB_V
-#define REV1_MINB_V 6
-#endif
-#ifndef REV1_V_HEAT
-#define REV1_V_HEAT 2
-#endif
 
 // number of kernels this library has launched in this process (diagnostic: bench.py
 // reports it as gpu_launches)
@@ -113,37 +107,11 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __re
 
 // DgmRev1Fn (hidden size 128) that also forms grad[U | b] of the Z, G and H gates -- the input-map
 // adjoint of the three pre-activation cotangents it has just computed -- so that the weight-gradient
-// kernel has no A^T E work left.  The grid stride is a multiple of 128: a thread keeps its unit j.
-// part[blk][gate 0..2 = Z, G, H][e 0..2 = U[:,0], U[:,1], b][128]
-template <class CS>
-struct Rev1Sink {   // slot 3 = H, 1 = G, 0 = Z -> rows 2, 1, 0 of g
-  float x0, x1; float (*g)[3];
-  __device__ __forceinline__ void operator()(int slot, const float* ab) const { input_map_adj<CS>(ab, x0, x1, g[slot == 3 ? 2 : slot]); }
-};
-template <class F, class CS, int MINB>
-__global__ void __launch_bounds__(EW_THREADS, MINB) rev1_e_kernel(const F f, const XSrc xs, int64_t n, float* __restrict__ part) {
-  float g[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float* x = xs.at(i >> 7);
-    Rev1Sink<CS> sink;
-    sink.x0 = __ldg(x); sink.x1 = (xs.d > 1) ? __ldg(x + 1) : 0.f; sink.g = g;
-    f.run(i, sink);
-  }
-  __shared__ float sm[9][EW_THREADS];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) sm[k][threadIdx.x] = g[k / 3][k % 3];
-  __syncthreads();
-  if (threadIdx.x < 128) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k)
-      part[((int64_t)blockIdx.x * 9 + k) * 128 + threadIdx.x] = sm[k][threadIdx.x] + sm[k][threadIdx.x + 128];
-  }
-}
-
-// V units per thread (8- / 16-byte accesses): the scalar version of the value-only stage ran at 0.74 of the
-// measured HBM peak, four units per thread took 2.7 ms off the step.  Thread = unit group q = tid % (128 / V)
-// for its whole life; 2 V threads of a block share a group.  Same part layout as rev1_e_kernel.
+// kernel has no A^T E work left.  part[blk][gate 0..2 = Z, G, H][e 0..2 = U[:,0], U[:,1], b][128]
+// V units per thread (8- / 16-byte accesses): with one unit per thread the value-only stage ran at 0.74 of
+// the measured HBM peak; V = 4 / 2 took 3.8 ms off the step.  The grid stride is a multiple of 128 / V: a
+// thread keeps its unit group q = tid % (128 / V) and nine running sums per unit for its whole life; 2 V
+// threads of a block share a group.
 template <class CS, int V>
 struct Rev1SinkV {
   float x0, x1; float (*g)[3][3];
@@ -445,29 +413,18 @@ struct CudaBackend {
     const int64_t n = rows * 128;
     if (n <= 0) return;
     if constexpr (!(CS::C == 1 || CS::C == 2 || CS::C == 4)) { if (!err) err = "internal: fused path called with an unsupported channel set"; return; } else {
-    int64_t blocks = (n + EW_THREADS - 1) / EW_THREADS;
-    // the value-only stage is light: more resident blocks (loads in flight) matter more than registers
-    constexpr int MINB = (CS::C == 1) ? REV1_MINB_V : 4;
-    int64_t cap = (int64_t)sms * MINB;   // one resident wave; a thread keeps its unit and its running sums
+    // units per thread: 4 (value-only and ODE / FHN rows), 2 (heat: four channels per unit)
+    constexpr int V = (CS::C <= 2) ? 4 : 2;
+    constexpr int MB = (CS::C == 1) ? 3 : 2;   // resident blocks per SM (80 / 126 registers)
+    const int64_t nv = rows * (128 / V);
+    int64_t blocks = (nv + EW_THREADS - 1) / EW_THREADS;
+    int64_t cap = (int64_t)sms * MB;            // one resident wave
     if (cap > part_n / (9 * 128)) cap = part_n / (9 * 128);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) { if (!err) err = "internal: partial buffer too small"; return; }
-    // units per thread: 4 (value-only and ODE / FHN rows), 2 (heat: four channels per unit)
-    constexpr int V = (CS::C <= 2) ? 4 : (CS::C == 4 ? REV1_V_HEAT : 1);
-    if constexpr (V > 1) {
-      constexpr int MB = (CS::C == 1) ? 3 : 2;
-      const int64_t nv = rows * (128 / V);
-      int64_t bv = (nv + EW_THREADS - 1) / EW_THREADS;
-      int64_t capv = (int64_t)sms * MB;
-      if (capv > part_n / (9 * 128)) capv = part_n / (9 * 128);
-      if (bv > capv) bv = capv;
-      blocks = bv;
+    {
       ProfScope ps(PC_EW, st, 0.0, 0.0);
       rev1_ev_kernel<F, CS, V, MB><<<(unsigned)blocks, EW_THREADS, 0, st>>>(f, xs, nv, part);
-      post();
-    } else {
-      ProfScope ps(PC_EW, st, 0.0, 0.0);
-      rev1_e_kernel<F, CS, MINB><<<(unsigned)blocks, EW_THREADS, 0, st>>>(f, xs, n, part);
       post();
     }
     reduce_gate_e(part, (int)blocks, 3, 0, 1, 3, outE, 4 * 128);

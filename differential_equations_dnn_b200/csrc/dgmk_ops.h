@@ -307,12 +307,7 @@ struct DgmFwd2Fn {
 template <class CS, int ACT>
 struct DgmRev1Fn {
   const float* A4; const float* S; const float* SBn; float* AB4; float* SBp; int Hp;
-  struct NoSink { DGMK_HD void operator()(int, const float*) const {} };
-  DGMK_HD void operator()(int64_t i) const { run(i, NoSink{}); }
-  // sink(slot, ab): called with each pre-activation cotangent (slot 3 = H, 1 = G, 0 = Z) as soon as it
-  // exists (the CUDA backend's fused variant forms grad[U | b] from them: input_map_adj)
-  template <class Sink>
-  DGMK_HD void run(int64_t i, Sink&& sink) const {
+  DGMK_HD void operator()(int64_t i) const {
     int64_t p = idiv(i, Hp); int j = (int)(i - p * Hp);
     const int64_t ld = 4 * (int64_t)Hp;
     const float* row = A4 + (p * CS::C) * ld + j;
@@ -335,24 +330,21 @@ struct DgmRev1Fn {
     act_adj<CS, ACT>(yb, afh, ab);
 #pragma unroll
     for (int c = 0; c < CS::C; ++c) orow[c * ld + 3 * Hp] = ab[c];
-    sink(3, ab);
     prod_adj<CS, false>(nb, h, yb);    // -(Gbar)
 #pragma unroll
     for (int c = 0; c < CS::C; ++c) yb[c] = -yb[c];
     act_adj<CS, ACT>(yb, afg, ab);
 #pragma unroll
     for (int c = 0; c < CS::C; ++c) orow[c * ld + Hp] = ab[c];
-    sink(1, ab);
     prod_adj<CS, false>(nb, s, yb);    // Zbar
     act_adj<CS, ACT>(yb, afz, ab);
 #pragma unroll
     for (int c = 0; c < CS::C; ++c) orow[c * ld] = ab[c];
-    sink(0, ab);
     prod_adj<CS, false>(nb, z, yb);    // direct path to s
 #pragma unroll
     for (int c = 0; c < CS::C; ++c) SBp[sb + (int64_t)c * Hp] = yb[c];
   }
-  // the same arithmetic on values already in registers (run4 below)
+  // the same arithmetic on values already in registers (runv below)
   DGMK_HD static void core(const float* afz, const float* afg, const float* afh, const float* s, const float* nb,
                            float* abz, float* abg, float* abh, float* sbp) {
     float z[CS::C], omg[CS::C], h[CS::C], yb[CS::C];
@@ -373,7 +365,8 @@ struct DgmRev1Fn {
     prod_adj<CS, false>(nb, z, sbp);   // direct path to s
   }
   // V = 2 or 4 consecutive units of one point (Hp % V == 0): 8- / 16-byte accesses, the index division once
-  // per V elements; k = p * (Hp/V) + j/V.  sink(u, slot, ab) as in run(), u = unit within the group
+  // per V elements; k = p * (Hp/V) + j/V.  sink(u, slot, ab) is called with each pre-activation cotangent
+  // (slot 3 = H, 1 = G, 0 = Z; u = unit within the group): the CUDA backend forms grad[U | b] from them
   template <int V> struct alignas(4 * V) Vec { float v[V]; };
   template <int V, class Sink>
   DGMK_HD void runv(int64_t k, Sink&& sink) const {
