@@ -83,3 +83,111 @@ struct HostBackend {
 }  // namespace
 
 DGMK_DEFINE_C_API(HostBackend, "host-emulation (tests only)")
+
+// ---- unit checks of functor code that only the CUDA backend's fused path calls (same templates, host
+// instantiation): the structural input-map adjoint and the V-units-per-thread DgmRev1 stage ------------------
+namespace {
+struct Lcg {   // deterministic, platform-independent
+  uint64_t s;
+  explicit Lcg(unsigned seed) : s(seed * 2654435761u + 12345u) {}
+  float uni() { s = s * 6364136223846793005ull + 1442695040888963407ull; return (float)((s >> 40) & 0xFFFFFF) / 16777216.0f; }
+};
+
+// max |input_map_adj sums - Abar^T E| / (1 + max |Abar^T E|) over random points (E rows from ExtInputFn)
+template <class CS>
+double check_input_map_adj(int npoints, int d, unsigned seed) {
+  Lcg r(seed);
+  std::vector<float> X((size_t)npoints * d), E((size_t)npoints * CS::C * 4);
+  for (auto& v : X) v = 3.0f * r.uni() - 1.0f;
+  dgmk::XSrc xs = dgmk::xsrc1(X.data(), npoints, d);
+  dgmk::ExtInputFn<CS> fe; fe.xs = xs; fe.E = E.data();
+  for (int p = 0; p < npoints; ++p) fe(p);
+  float g[3] = {0.f, 0.f, 0.f};
+  double ref[4] = {0, 0, 0, 0};
+  for (int p = 0; p < npoints; ++p) {
+    float ab[CS::C];
+    for (int c = 0; c < CS::C; ++c) ab[c] = 2.0f * r.uni() - 1.0f;
+    const float* x = xs.at(p);
+    dgmk::input_map_adj<CS>(ab, x[0], d > 1 ? x[1] : 0.f, g);
+    for (int c = 0; c < CS::C; ++c)
+      for (int e = 0; e < 4; ++e) ref[e] += (double)ab[c] * E[((size_t)p * CS::C + c) * 4 + e];
+  }
+  double worst = std::fabs(ref[3]), scale = 1.0;   // the fourth E column is structurally zero
+  for (int e = 0; e < 3; ++e) scale = std::fmax(scale, 1.0 + std::fabs(ref[e]));
+  for (int e = 0; e < 3; ++e) worst = std::fmax(worst, std::fabs((double)g[e] - ref[e]));
+  return worst / scale;
+}
+
+template <class CS, int V>
+struct SumSink {
+  float x0, x1; double (*g)[3][3];
+  void operator()(int u, int slot, const float* ab) const {
+    float t[3] = {0.f, 0.f, 0.f};
+    dgmk::input_map_adj<CS>(ab, x0, x1, t);
+    for (int e = 0; e < 3; ++e) g[u][slot == 3 ? 2 : slot][e] += t[e];
+  }
+};
+// DgmRev1Fn::runv<V> against operator(): 0 = stored cotangents bit-identical and the sink saw exactly them,
+// 1 = stored values differ, 2 = sink sums differ
+template <class CS, int ACT, int V>
+int check_rev1_runv(int npoints, unsigned seed) {
+  constexpr int Hp = 8, C = CS::C;
+  Lcg r(seed);
+  const size_t M = (size_t)npoints * C;
+  std::vector<float> A4(M * 4 * Hp), S(M * Hp), SBn(M * Hp), ABa(M * 4 * Hp, -7.f), ABb(M * 4 * Hp, -7.f), SPa(M * Hp), SPb(M * Hp);
+  for (size_t i = 0; i < A4.size(); ++i) {
+    const bool value_row = ((i / (4 * Hp)) % C) == 0;
+    A4[i] = value_row ? (ACT == dgmk::ACT_TANH ? 1.8f * r.uni() - 0.9f : (r.uni() < 0.3f ? 0.f : r.uni())) : 2.0f * r.uni() - 1.0f;
+  }
+  for (auto& v : S) v = 2.0f * r.uni() - 1.0f;
+  for (auto& v : SBn) v = 2.0f * r.uni() - 1.0f;
+  dgmk::DgmRev1Fn<CS, ACT> fa; fa.A4 = A4.data(); fa.S = S.data(); fa.SBn = SBn.data(); fa.AB4 = ABa.data(); fa.SBp = SPa.data(); fa.Hp = Hp;
+  dgmk::DgmRev1Fn<CS, ACT> fb = fa; fb.AB4 = ABb.data(); fb.SBp = SPb.data();
+  for (int64_t i = 0; i < (int64_t)npoints * Hp; ++i) fa(i);
+  double g[V][3][3] = {};
+  for (int64_t k = 0; k < (int64_t)npoints * (Hp / V); ++k) {
+    SumSink<CS, V> sink; sink.x0 = 0.25f * (float)(k % 7); sink.x1 = -0.5f; sink.g = g;
+    fb.template runv<V>(k, sink);
+  }
+  if (memcmp(ABa.data(), ABb.data(), ABa.size() * 4) || memcmp(SPa.data(), SPb.data(), SPa.size() * 4)) return 1;
+  // what the sink was shown must be what was stored: redo its sums from the stored cotangents
+  double h[V][3][3] = {};
+  for (int64_t k = 0; k < (int64_t)npoints * (Hp / V); ++k) {
+    const int64_t p = k / (Hp / V); const int j0 = (int)(k % (Hp / V)) * V;
+    for (int u = 0; u < V; ++u)
+      for (int slot : {0, 1, 3}) {
+        float ab[C], t[3] = {0.f, 0.f, 0.f};
+        for (int c = 0; c < C; ++c) ab[c] = ABa[((size_t)p * C + c) * 4 * Hp + slot * Hp + j0 + u];
+        dgmk::input_map_adj<CS>(ab, 0.25f * (float)(k % 7), -0.5f, t);
+        for (int e = 0; e < 3; ++e) h[u][slot == 3 ? 2 : slot][e] += t[e];
+      }
+  }
+  for (int u = 0; u < V; ++u) for (int a = 0; a < 3; ++a) for (int e = 0; e < 3; ++e)
+    if (g[u][a][e] != h[u][a][e]) return 2;
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+double dgmk_emul_check_input_map_adj(int cs, int npoints, int d, unsigned seed) {
+  switch (cs) {
+    case dgmk::CS_V: return check_input_map_adj<dgmk::CsV>(npoints, d, seed);
+    case dgmk::CS_D1O1: return check_input_map_adj<dgmk::CsD1O1>(npoints, d, seed);
+    case dgmk::CS_HEAT: return check_input_map_adj<dgmk::CsHeat>(npoints, d, seed);
+    case dgmk::CS_D2O1: return check_input_map_adj<dgmk::CsD2O1>(npoints, d, seed);
+    case dgmk::CS_D1O2: return check_input_map_adj<dgmk::CsD1O2>(npoints, d, seed);
+    default: return check_input_map_adj<dgmk::CsD2O2>(npoints, d, seed);
+  }
+}
+int dgmk_emul_check_rev1_runv(int cs, int tanh_gates, int V, int npoints, unsigned seed) {
+#define DGMK_RV(CS)                                                                                         \
+  return tanh_gates ? (V == 4 ? check_rev1_runv<CS, dgmk::ACT_TANH, 4>(npoints, seed) : check_rev1_runv<CS, dgmk::ACT_TANH, 2>(npoints, seed)) \
+                    : (V == 4 ? check_rev1_runv<CS, dgmk::ACT_RELU, 4>(npoints, seed) : check_rev1_runv<CS, dgmk::ACT_RELU, 2>(npoints, seed));
+  switch (cs) {
+    case dgmk::CS_V: DGMK_RV(dgmk::CsV)
+    case dgmk::CS_D1O1: DGMK_RV(dgmk::CsD1O1)
+    default: DGMK_RV(dgmk::CsHeat)
+  }
+#undef DGMK_RV
+}
+}

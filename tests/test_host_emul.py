@@ -155,3 +155,25 @@ def test_errors(lib):
     assert rc == -2  # DGMK_EWORKSPACE
     rc = lib.dgmk_heat_step(C.byref(desc), P(theta), *[P(theta)] * 6, 64, 64, 1.0, P(loss), P(theta), P(ws), 256, None)
     assert rc == -1  # wrong dims for heat
+
+
+@pytest.mark.parametrize("cs,d", [(0, 1), (0, 2), (1, 1), (2, 2), (3, 2), (4, 1), (5, 2)])
+def test_input_map_adj_equals_abar_t_e(lib, cs, d):
+    """grad[U | b] formed from the point coordinates (dgmk_ops.h::input_map_adj: the structural zeros and ones
+    of the E rows folded in -- what the fused CUDA path accumulates next to the cotangents) equals Abar^T E with
+    the E rows ExtInputFn writes, for every channel set."""
+    lib.dgmk_emul_check_input_map_adj.restype = C.c_double
+    lib.dgmk_emul_check_input_map_adj.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint]
+    for seed in (1, 2):
+        assert lib.dgmk_emul_check_input_map_adj(cs, 300, d, seed) < 2e-6
+
+
+@pytest.mark.parametrize("cs", [0, 1, 2])
+@pytest.mark.parametrize("tanh_gates", [1, 0])
+@pytest.mark.parametrize("V", [2, 4])
+def test_rev1_units_per_thread_variant_is_bit_identical(lib, cs, tanh_gates, V):
+    """DgmRev1Fn::runv<V> (V units per call: the CUDA backend's rev1_ev_kernel) stores exactly what the
+    one-unit functor stores, and hands its sink exactly those cotangents."""
+    lib.dgmk_emul_check_rev1_runv.restype = C.c_int
+    lib.dgmk_emul_check_rev1_runv.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint]
+    assert lib.dgmk_emul_check_rev1_runv(cs, tanh_gates, V, 37, 5) == 0
