@@ -83,7 +83,7 @@ def spec_arr(spec):
     return np.array([spec.kind, spec.d, spec.o, spec.H, spec.L, spec.act], dtype=np.int64)
 
 
-def run_both(net, fn):
+def run_both(net, fn, keep64=False):
     """fn(net, cast) -> loss ; run in fp32 then fp64."""
     out = {}
     for tag, dt in (("", torch.float32), ("_f64", torch.float64)):
@@ -93,7 +93,7 @@ def run_both(net, fn):
         loss.backward()
         g, live = flat_grad(n)
         out["loss" + tag] = loss.detach().numpy()
-        if dt == torch.float32 or g.numel() <= 100_000:  # keep big fixtures small
+        if dt == torch.float32 or g.numel() <= 100_000 or keep64:  # keep big fixtures small
             out["grad" + tag] = g.numpy()
         out["live"] = live.numpy()
     net.float()
@@ -110,7 +110,12 @@ def heat_inputs(B, gen):
     return X, X0, XBD1, XBD2, torch.zeros(B, 1), torch.zeros(B, 1)
 
 
+ONLY = None  # `python oracle/make_golden.py NAME [NAME...]` regenerates just those fixtures
+
+
 def save(name, **kw):
+    if ONLY and name not in ONLY:
+        return
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, **kw)
@@ -126,6 +131,9 @@ def main():
     heat_cases = {
         "heat_dgm_h32l1": (S(DGL, 2, 1, 32, 1, rp.ACT_TANH), 64),
         "heat_dgm_h128l3": (S(DGL, 2, 1, 128, 3, rp.ACT_TANH), 24),
+        # several 64-row tiles of the fused tcgen05 kernels plus a ragged tail (203 = 3 * 64 + 11 rows:
+        # 812 jet rows / 609 companion rows)
+        "heat_dgm_h128l3_b203": (S(DGL, 2, 1, 128, 3, rp.ACT_TANH), 203),
         "heat_dgm_h50l3": (S(DGL, 2, 1, 50, 3, rp.ACT_TANH), 37),
         "heat_mlp_tanh_h128l3": (S(MLP, 2, 1, 128, 3, rp.ACT_TANH), 64),
         "heat_mlp_relu_h128l3": (S(MLP, 2, 1, 128, 3, rp.ACT_RELU), 64),
@@ -134,6 +142,8 @@ def main():
         "heat_dgmraw_h32l2": (S(DGR, 2, 1, 32, 2, rp.ACT_RELU), 64),
     }
     for name, (spec, B) in heat_cases.items():
+        if ONLY and name not in ONLY:
+            continue
         net = build(ref, spec, 1234)
         gen = torch.Generator().manual_seed(1)
         inp = heat_inputs(B, gen)
@@ -142,7 +152,7 @@ def main():
             a = [z.to(dt) for z in inp]
             a[0] = a[0].clone().requires_grad_(True)
             return ref["heat"].dgm_loss_func(n, *a)
-        r = run_both(net, fn)
+        r = run_both(net, fn, keep64=name.endswith("_b203"))
         save(name, spec=spec_arr(spec), theta=flat(net).numpy(),
              X=inp[0].numpy(), X0=inp[1].numpy(), XBD1=inp[2].numpy(),
              XBD2=inp[3].numpy(), x_bd1=inp[4].numpy(), x_bd2=inp[5].numpy(), **r)
@@ -272,4 +282,5 @@ def main():
 
 
 if __name__ == "__main__":
+    ONLY = set(sys.argv[1:]) or None
     main()

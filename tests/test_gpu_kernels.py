@@ -109,7 +109,7 @@ def test_jets_and_eval(K, name):
         if order >= 1:
             assert rel(J.cpu().numpy(), g["J"]) < TOL
         if order >= 2:
-            assert rel(Hs.cpu().numpy(), g["Hs"]) < 5 * TOL
+            assert rel(Hs.cpu().numpy(), g["Hs"]) < TOL   # the FP32 reference itself: 1.4e-7 .. 2.3e-7 vs these FP64 values
     assert rel(K.evaluate(d, th, X).cpu().numpy(), g["y"]) < TOL
 
 
@@ -242,9 +242,21 @@ def test_engines_agree(K, kind, prob):
     finally:
         lib.dgmk_set_gemm_engine(1)
     # ReLU gates (neural_networks.DGM): a pre-activation within FP32 rounding of 0 lands on the other side of
-    # the kink than in FP64 and flips that row's derivative -- the FP32 reference itself is only within a few
-    # 1e-5 of FP64 there, every engine alike
-    tol = 1e-4 if kind == "dgmraw" else TOL
+    # the kink than in FP64 and flips that row's derivative.  The bar is therefore what the reference's own
+    # FP32 arithmetic achieves against FP64 on these inputs (oracle/ref_port in FP32 on this GPU, cuBLAS, TF32
+    # off), measured here: max(1e-5, 2 x that), never more than 1e-4
+    tol = TOL
+    if kind == "dgmraw":
+        from oracle import ref_port as rp
+        torch.backends.cuda.matmul.allow_tf32 = False
+        rspec = rp.NetSpec(*[int(v) for v in spec])
+        lfn = rp.fredholm_loss if prob == "fredholm" else rp.heat_loss
+        l32, g32 = rp.loss_and_grad(lfn, rspec, net.flat_theta(), *args)
+        g32 = g32.double().cpu().numpy()
+        worst = max(rel(g32[off:off + n], go[off:off + n]) for (_, off, n, live) in net.param_slices()
+                    if live and np.linalg.norm(go[off:off + n]) > 0)
+        tol = max(TOL, 2 * worst, 2 * abs(float(l32) - lo) / abs(lo))
+        assert tol <= 1e-4, tol
     for eng in (0, 2, 1):
         assert abs(out[eng][-1] - lo) <= tol * abs(lo), (eng, out[eng][-1], lo)
         for (_, off, n, live) in net.param_slices():

@@ -117,3 +117,152 @@ def test_fredholm_k1024_tall_operands():
         parts = parts + K.fredholm_step(d, theta, x[lo:hi].contiguous(), T[:, lo:hi].contiguous(), B_global=B).double().cpu().numpy()
     assert abs(parts[-1] - whole[-1]) <= 1e-5 * abs(whole[-1])
     assert np.linalg.norm(parts[:-1] - whole[:-1]) <= 1e-5 * np.linalg.norm(whole[:-1])
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE-size parity against the torch-autograd oracle executed ON THE GPU (SURVEY 8c tier 3:
+# oracle/ref_port = the reference's nested-autograd algorithm, FP32 cuBLAS with TF32 off), chunk-
+# accumulated so that the double-backward graph fits.  Bar: loss and per-tensor norm-wise gradient
+# within 1e-5 (north_star).  For ReLU networks the FP32 reference itself is only kink-stable to what
+# its own FP32-vs-FP64 difference shows (a pre-activation within rounding of 0 flips a derivative), so
+# there the bar is max(1e-5, 2 x ||ref32 - ref64||) with both references computed in the test.
+def _ref_chunked(loss_fn, spec, theta, args, B, CH, slicer, dtype=torch.float32):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    gsum = torch.zeros_like(theta, dtype=torch.float64)
+    lsum = 0.0
+    for lo in range(0, B, CH):
+        hi = min(B, lo + CH)
+        th = theta.detach().to(dtype).clone().requires_grad_(True)
+        l = loss_fn(spec, th, *[z.to(dtype) for z in slicer(args, lo, hi)]) * ((hi - lo) / B)
+        l.backward()
+        gsum += th.grad.double()
+        lsum += float(l.item())
+    return lsum, gsum.cpu().numpy()
+
+
+def _rows(args, lo, hi):
+    return [z[lo:hi] for z in args]
+
+
+def _check(out, lref, gref, layout, tol, tag=""):
+    out = out.double().cpu().numpy()
+    assert abs(out[-1] - lref) <= tol * abs(lref), (tag, out[-1], lref)
+    worst = 0.0
+    for off, n, live in layout:
+        if live and np.linalg.norm(gref[off:off + n]) > 0:
+            worst = max(worst, rel(out[off:off + n], gref[off:off + n]))
+    assert worst < tol, (tag, worst)
+    return worst
+
+
+def _layout(net):
+    return [(off, n, live) for _, off, n, live in net.param_slices()]
+
+
+def test_heat_dgm128_full_2_20_vs_oracle():
+    """BASELINE configs[1] at its full size: heat + dgm_net.DGM(2,1,128,3), 2^20 rows, 16 chunks of 65536."""
+    from oracle import ref_port as rp
+    from differential_equations_dnn_b200 import kernels as K
+    net = make(128, 3)
+    B = 1 << 20
+    a = heat_inputs(B, 21)
+    out = K.heat_step(net.desc, net.flat_theta(), *a)
+    spec = rp.NetSpec(rp.KIND_DGM_LINEAR, 2, 1, 128, 3, rp.ACT_TANH)
+    lref, gref = _ref_chunked(rp.heat_loss, spec, net.flat_theta(), a, B, 1 << 16, _rows)
+    _check(out, lref, gref, _layout(net), 1e-5, "heat 2^20")
+
+
+@pytest.mark.parametrize("kind", ["mlp", "dgm"])
+def test_fhn_full_2_20_vs_oracle(kind):
+    """BASELINE configs[2]: FitzHugh-Nagumo loss at 2^20 time points, MLP(1,2,128,3,tanh) (the config) and the
+    as-shipped dgm_net.DGM(1,2,128,4) (fitzhugh_nagumo.py:53-97, :211-214)."""
+    from oracle import ref_port as rp
+    from differential_equations_dnn_b200 import kernels as K, dgm_net, neural_networks
+    torch.manual_seed(1234)
+    if kind == "mlp":
+        net = neural_networks.MLP(1, 2, 128, 3, activation="tanh").cuda()
+        spec = rp.NetSpec(rp.KIND_MLP, 1, 2, 128, 3, rp.ACT_TANH)
+    else:
+        net = dgm_net.DGM(1, 2, 128, 4).cuda()
+        spec = rp.NetSpec(rp.KIND_DGM_LINEAR, 1, 2, 128, 4, rp.ACT_TANH)
+    B = 1 << 20
+    gen = torch.Generator().manual_seed(22)
+    a = [(30.01 * torch.rand([B, 1], generator=gen)).cuda(), torch.zeros(B, 1).cuda(), torch.zeros(B, 2).cuda()]
+    out = K.fhn_step(net.desc, net.flat_theta(), *a)
+    lref, gref = _ref_chunked(rp.fhn_loss, spec, net.flat_theta(), a, B, 1 << 16, _rows)
+    _check(out, lref, gref, _layout(net), 1e-5, "fhn 2^20 " + kind)
+
+
+@pytest.mark.parametrize("act", ["relu", "tanh"])
+def test_ode_full_2_20_vs_oracle(act):
+    """BASELINE configs[0] at the throughput size: simple_ode loss, MLP(1,1,32) (relu as shipped,
+    simple_ode.py:167; tanh variant), 2^20 rows."""
+    from oracle import ref_port as rp
+    from differential_equations_dnn_b200 import kernels as K, neural_networks
+    torch.manual_seed(1234)
+    net = neural_networks.MLP(1, 1, 32, 1, activation=act).cuda()
+    spec = rp.NetSpec(rp.KIND_MLP, 1, 1, 32, 1, rp.ACT_NAMES[act])
+    B = 1 << 20
+    gen = torch.Generator().manual_seed(23)
+    a = [(1.01 * torch.rand([B, 1], generator=gen)).cuda(), torch.zeros(B, 1).cuda(), 2.0 * torch.ones(B, 1).cuda()]
+    out = K.ode_step(net.desc, net.flat_theta(), *a)
+    l32, g32 = _ref_chunked(rp.ode_loss, spec, net.flat_theta(), a, B, 1 << 18, _rows)
+    tol = 1e-5
+    if act == "relu":   # kink stability of the FP32 reference itself (see the header comment)
+        l64, g64 = _ref_chunked(rp.ode_loss, spec, net.flat_theta(), a, B, 1 << 18, _rows, torch.float64)
+        tol = max(tol, 2 * rel(g32, g64), 2 * abs(l32 - l64) / abs(l64))
+        assert tol < 1e-4, tol
+        _check(out, l64, g64, _layout(net), tol, "ode 2^20 relu vs fp64")
+    _check(out, l32, g32, _layout(net), tol, "ode 2^20 " + act)
+
+
+def test_fredholm_k1024_vs_oracle():
+    """BASELINE configs[3]: neural_networks.DGM(1,1,32) (ReLU gates, raw parameters), k = 1024 quadrature nodes
+    per point, B = 2^12 points = 4.2 M node evaluations per step (fredholm.py:47-74)."""
+    from oracle import ref_port as rp
+    from differential_equations_dnn_b200 import kernels as K, neural_networks
+    torch.manual_seed(1234)
+    net = neural_networks.DGM(1, 1, 32, 1).cuda()
+    # biases start at exactly 0 there (neural_networks.py:93-96): the reference init, ReLU ties included
+    spec = rp.NetSpec(rp.KIND_DGM_RAW, 1, 1, 32, 1, rp.ACT_RELU)
+    B, k = 1 << 12, 1024
+    gen = torch.Generator().manual_seed(24)
+    x = ((np.pi / 2) * torch.rand(B, 1, generator=gen)).cuda()
+    T = ((np.pi / 2) * torch.rand(k, B, 1, generator=gen)).cuda()
+    out = K.fredholm_step(net.desc, net.flat_theta(), x, T)
+
+    def sl(args, lo, hi):
+        return [args[0][lo:hi], args[1][:, lo:hi]]
+    l32, g32 = _ref_chunked(rp.fredholm_loss, spec, net.flat_theta(), [x, T], B, 1 << 11, sl)
+    l64, g64 = _ref_chunked(rp.fredholm_loss, spec, net.flat_theta(), [x, T], B, 1 << 11, sl, torch.float64)
+    tol = max(1e-5, 2 * rel(g32, g64), 2 * abs(l32 - l64) / abs(l64))
+    assert tol < 1e-4, tol
+    _check(out, l64, g64, _layout(net), tol, "fredholm k=1024 vs fp64")
+    _check(out, l32, g32, _layout(net), tol, "fredholm k=1024 vs fp32")
+
+
+def test_fhn_shipped_grid_sampler():
+    """The shipped FitzHugh-Nagumo sampler (fitzhugh_nagumo.py:123-133: `batch_size` distinct nodes of a
+    200-point grid drawn with torch.multinomial) on the GPU: the first iteration's loss equals the oracle's on
+    the same draw, and the driver runs (eagerly and replayed from a CUDA graph)."""
+    from oracle import ref_port as rp
+    from differential_equations_dnn_b200 import dgm_net, fitzhugh_nagumo as fz
+    spec = rp.NetSpec(rp.KIND_DGM_LINEAR, 1, 2, 32, 2, rp.ACT_TANH)
+    bs = 100   # the CLI default (fitzhugh_nagumo.py:202-204)
+    y_ic = torch.zeros(bs, 2, device="cuda")
+    for graph in (False, True):
+        torch.manual_seed(1234)
+        net = dgm_net.DGM(1, 2, 32, 2).cuda()
+        theta0 = net.flat_theta().clone()
+        torch.manual_seed(77)
+        _, losses = fz.minimize_loss_dgm(net, y_ic, iterations=40, batch_size=bs, lrate=1e-3, sampler="grid", cuda_graph=graph)
+        assert len(losses) == 40 and np.all(np.isfinite(losses))
+        torch.manual_seed(77)   # replay the first draw
+        Tg = torch.linspace(0.0, 30.0, steps=200, device="cuda")
+        prob = torch.full((200,), 1.0 / 200, device="cuda")
+        t = Tg[prob.multinomial(num_samples=bs, replacement=False)].reshape(-1, 1)
+        assert t.unique().numel() == bs
+        l0 = rp.fhn_loss(spec, theta0, t, torch.zeros(bs, 1, device="cuda"), y_ic)
+        assert abs(losses[0] - l0.item()) <= 1e-5 * abs(l0.item()), (graph, losses[0], l0.item())
+        assert np.mean(losses[-5:]) < np.mean(losses[:5])
