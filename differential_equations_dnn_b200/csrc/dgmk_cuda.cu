@@ -3,6 +3,7 @@
 //        --expt-relaxed-constexpr -Xcompiler -fPIC -shared -o libdgmk.so dgmk_cuda.cu
 // This is the only implementation the package loads: there is no CPU path.
 #include <cuda_runtime.h>
+#include <atomic>
 #include <vector>
 #include "dgmk_capi_impl.h"
 #include "dgmk_gemm.cuh"
@@ -283,6 +284,11 @@ struct CudaBackend {
   int sms;
   bool use_tc, fuse;
   int64_t hl_stride = 0;  // distance between the plain / tf32-hi / tf32-lo copies of the packed weights
+  // design bytes (operands read + results written, each once) of the NEXT element-wise / reduction launch,
+  // announced by the pipeline for the per-class traffic accounting of dgmk_profile
+  double pending_bytes = 0.0;
+  void note_bytes(double b) { pending_bytes = b; }
+  double take_bytes() { double b = pending_bytes; pending_bytes = 0.0; return b; }
   explicit CudaBackend(void* stream) : st((cudaStream_t)stream), err(nullptr), sms(148), use_tc(g_use_tc), fuse(g_fuse) {
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) {
@@ -291,6 +297,17 @@ struct CudaBackend {
     }
   }
   void note(cudaError_t e) { if (e != cudaSuccess && !err) err = cudaGetErrorString(e); }
+  // true exactly once per (kernel family `slot`, current device): cudaFuncSetAttribute opt-ins are per device.
+  // Setting the attribute twice is harmless, so a relaxed race between threads only repeats the call.
+  bool first_use_on_device(int slot) {
+    static std::atomic<unsigned long long> masks[8];
+    int dev = 0;
+    note(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (masks[slot].load(std::memory_order_acquire) & bit) return false;
+    masks[slot].fetch_or(bit, std::memory_order_release);
+    return true;
+  }
   void post() { ++g_launches; note(cudaPeekAtLastError()); }
 
   template <class F>
@@ -299,7 +316,7 @@ struct CudaBackend {
     int64_t blocks = (n + EW_THREADS - 1) / EW_THREADS;
     int64_t cap = (int64_t)sms * 32;
     if (blocks > cap) blocks = cap;
-    ProfScope ps(PC_EW, st, 0.0, 0.0);
+    ProfScope ps(PC_EW, st, 0.0, take_bytes());
     ew_kernel<F><<<(unsigned)blocks, EW_THREADS, 0, st>>>(f, n);
     post();
   }
@@ -311,7 +328,7 @@ struct CudaBackend {
     int64_t blocks = (n4 + EW_THREADS - 1) / EW_THREADS;
     int64_t cap = (int64_t)sms * 32;
     if (blocks > cap) blocks = cap;
-    ProfScope ps(PC_EW, st, 0.0, 0.0);
+    ProfScope ps(PC_EW, st, 0.0, take_bytes());
     ew4_kernel<F><<<(unsigned)blocks, EW_THREADS, 0, st>>>(f, n4);
     post();
   }
@@ -330,11 +347,9 @@ struct CudaBackend {
     if (M <= 0) return;
     ProfScope ps(PC_STREAM_NN, st, 2.0 * M * N * K, 4.0 * M * (K + (acc ? 2.0 : 1.0) * N));
     if (use_tc && N % tc::BN == 0 && K % tc::KC == 0) {
-      static bool attr_done = false;
-      if (!attr_done) {
+      if (first_use_on_device(0)) {   // the opt-in is per function AND per device
         note(cudaFuncSetAttribute(tc::gemm_nn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         note(cudaFuncSetAttribute(tc::gemm_nn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-        attr_done = true;
       }
       dim3 grid(N / tc::BN, (unsigned)((M + tc::BM - 1) / tc::BM));
       if (acc) tc::gemm_nn_tc_kernel<true><<<grid, tc::NT, tc::SMEM_BYTES, st>>>(A, lda, Bt, ldbt, hl_stride, C, ldc, M, K);
@@ -362,12 +377,12 @@ struct CudaBackend {
     if (M <= 0) return 0;
     ProfScope ps(PC_LANE, st, 2.0 * M * lg::NU * lg::KTOT * ngates, units * M * lg::KTOT * 4.0);
     // opt-in shared memory size: per function and per device
-    static unsigned long long done_mask = 0;
+    static std::atomic<unsigned long long> done_mask{0};   // one per EPI instantiation
     int dev = 0;
     note(cudaGetDevice(&dev));
-    if (!((done_mask >> (dev & 63)) & 1ull)) {
+    if (!((done_mask.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
       note(cudaFuncSetAttribute(lg::lane_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, lg::SMEM_BYTES));
-      done_mask |= 1ull << (dev & 63);
+      done_mask.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
     const int64_t ntiles = (M + lg::NR - 1) / lg::NR;
     int64_t grid, c0 = 0, c1 = 0;
@@ -423,7 +438,7 @@ struct CudaBackend {
     if (blocks > cap) blocks = cap;
     if (blocks < 1) { if (!err) err = "internal: partial buffer too small"; return; }
     {
-      ProfScope ps(PC_EW, st, 0.0, 0.0);
+      ProfScope ps(PC_EW, st, 0.0, 9.0 * rows * CS::C * 128 * 4.0);   // read s'bar, Z, G, H, s; write abar_Z, abar_G, abar_H, s bar
       rev1_ev_kernel<F, CS, V, MB><<<(unsigned)blocks, EW_THREADS, 0, st>>>(f, xs, nv, part);
       post();
     }
@@ -431,7 +446,7 @@ struct CudaBackend {
     }
   }
   void reduce_gate_e(const float* part, int nparts, int ngates, int gm0, int gm1, int gm2, float* out, int64_t ldo) {
-    ProfScope ps(PC_OTHER, st, 0.0, 0.0);
+    ProfScope ps(PC_OTHER, st, 0.0, 4.0 * nparts * ngates * 384);
     reduce_gate_e_kernel<<<(unsigned)((ngates * 384 + 31) / 32), dim3(32, nparts >= 512 ? 32 : 8), 0, st>>>(part, nparts, ngates, gm0, gm1, gm2, out, ldo);
     post();
   }
@@ -453,7 +468,7 @@ struct CudaBackend {
     if (cols <= 0) { cols = (int)n; ldo = n; }
     // slices: enough to keep every chain short, few enough that small partial counts are not split to nothing
     const int S = nparts >= 512 ? 32 : (nparts >= 128 ? 16 : (nparts >= 16 ? 8 : 1));
-    ProfScope ps(PC_OTHER, st, 0.0, 0.0);
+    ProfScope ps(PC_OTHER, st, 0.0, 4.0 * nparts * (double)n);
     reduce_partials_kernel<<<(unsigned)((n + 31) / 32), dim3(32, S), 0, st>>>(part, nparts, n, out, cols, ldo);
     post();
   }
@@ -498,15 +513,11 @@ struct CudaBackend {
       const int64_t nparts = (M + seg_rows - 1) / seg_rows;   // segments that contain rows (the rest is never written)
       float* PEw = E ? part + ctas * nseg * tile : nullptr;
       dim3 gws(Kd / 128, N / 128, (unsigned)ctas);
-      static unsigned long long done_mask = 0;
-      int dev = 0;
-      note(cudaGetDevice(&dev));
-      if (!((done_mask >> (dev & 63)) & 1ull)) {
+      if (first_use_on_device(2)) {
         note(cudaFuncSetAttribute(wg::wgrad_ws_kernel<512, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES));
         note(cudaFuncSetAttribute(wg::wgrad_ws_kernel<128, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES));
         note(cudaFuncSetAttribute(wg::wgrad_ws_kernel<512, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES_SEP));
         note(cudaFuncSetAttribute(wg::wgrad_ws_kernel<128, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES_SEP));
-        done_mask |= 1ull << (dev & 63);
       }
       ProfScope ps(PC_WGRAD, st, 2.0 * M * N * Kd, 4.0 * M * (N + Kd + (E ? 4.0 : 0.0)));
       // without the A^T E side product: the variant with its own MMA-issuer warpgroup
@@ -524,10 +535,8 @@ struct CudaBackend {
     }
     dim3 grid(Kd / BN, (N + GEMM_BM - 1) / GEMM_BM, (unsigned)splits);
     if (use_tc && E && N % tc::BM == 0 && Kd % tc::BN == 0) {
-      static bool attr_done = false;
-      if (!attr_done) {
+      if (first_use_on_device(1)) {
         note(cudaFuncSetAttribute(tctn::gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tctn::TN_SMEM_BYTES));
-        attr_done = true;
       }
       tctn::gemm_tn_tc_kernel<<<grid, tctn::NT, tctn::TN_SMEM_BYTES, st>>>(A, lda, S, lds, E, part, PE, N, Kd, M, rps);
     } else if (BN == 128) gemm_tn_kernel<128><<<grid, GEMM_NT, 0, st>>>(A, lda, S, lds, part, N, Kd, M, rps, E, PE);
@@ -557,7 +566,7 @@ struct CudaBackend {
     nblk = (M + rpb - 1) / rpb;
     dim3 grid(ctiles, (unsigned)nblk);
     {
-      ProfScope ps(PC_OTHER, st, 0.0, 0.0);
+      ProfScope ps(PC_OTHER, st, 0.0, 4.0 * M * (N + (Wt ? 4.0 : 0.0)));
       if (Wt) wcolsum_kernel<true><<<grid, 128, 0, st>>>(Mat, ldm, N, Wt, M, rpb, part);
       else wcolsum_kernel<false><<<grid, 128, 0, st>>>(Mat, ldm, N, Wt, M, rpb, part);
       post();
@@ -570,7 +579,7 @@ struct CudaBackend {
     int64_t blocks = (M + 7) / 8;
     int64_t cap = (int64_t)sms * 16;
     if (blocks > cap) blocks = cap;
-    ProfScope ps(PC_OTHER, st, 0.0, 0.0);
+    ProfScope ps(PC_OTHER, st, 0.0, 4.0 * M * (Hp + 4.0));
     rowdot_kernel<<<(unsigned)blocks, 256, 0, st>>>(S, lds, W, b, U, M, Hp, o, C);
     post();
   }
@@ -582,7 +591,9 @@ struct CudaBackend {
     if (e != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
   }
-  const char* error() { note(cudaPeekAtLastError()); return err; }
+  // consumes the sticky-less CUDA error state so that a failed launch here does not leak into the caller's
+  // (PyTorch's) own launch checks or into later dgmk calls
+  const char* error() { note(cudaGetLastError()); return err; }
 };
 
 }  // namespace dgmk

@@ -153,6 +153,7 @@ struct Pipeline {
     bk.zero(c.Wp, (size_t)c.pl.w_total * 4 * 3);
     PackFn f; f.t = c.pack; f.theta = theta; f.packed = c.Wp; f.hl = c.pl.w_total;
     bk.hl_stride = c.pl.w_total;
+    bk.note_bytes(4.0 * num_params(c.n) * 7.0);
     bk.ew(f, num_params(c.n));
   }
   void zero_grads() { bk.zero(c.Gp, (size_t)c.pl.g_total * 4); }
@@ -168,10 +169,13 @@ struct Pipeline {
     const int Hp = n.Hp;
     const int64_t M = pb.M, R = pb.rows;
     DGMK_CS_SWITCH(pb.cs, CS, {
+      const double unit = 4.0 * (double)M * Hp;   // one [M, Hp] FP32 matrix
       ExtInputFn<CS> fe; fe.xs = pb.xs; fe.E = pb.E;
+      bk.note_bytes(R * (4.0 * n.d + 16.0 * pb.C));
       bk.ew(fe, R);
       DGMK_ACT_SWITCH(n.in_act(), ACT, {
         InputFwdFn<CS, ACT> f; f.xs = pb.xs; f.inb = inb(); f.S0 = pb.S[0]; f.Hp = Hp;
+        bk.note_bytes(unit);
         bk.ew4(f, R * Hp);
       })
       for (int l = 0; l < n.L; ++l) {
@@ -185,6 +189,7 @@ struct Pipeline {
           bk.gemm_nn(pb.S[l], Hp, c.Wp + c.pl.wf[l], Hp, c.Wp + c.pl.wb[l], Hp, pb.G[l], Hp, M, Hp, Hp, false);
           DGMK_ACT_SWITCH(n.act, ACT, {
             MlpActFn<CS, ACT> f; f.G = pb.G[l]; f.ub = ub(l); f.Yn = pb.S[l + 1]; f.Hp = Hp;
+            bk.note_bytes(3 * unit);
             bk.ew(f, R * Hp);
           })
         } else {
@@ -197,12 +202,14 @@ struct Pipeline {
           bk.gemm_nn(pb.S[l], Hp, c.Wp + c.pl.wf[l], 3 * Hp, c.Wp + c.pl.wb[l], Hp, pb.G[l], 4 * Hp, M, 3 * Hp, Hp, false);
           DGMK_GACT_SWITCH(n.gate_act(), ACT, {
             DgmFwd1Fn<CS, ACT> f; f.xs = pb.xs; f.A4 = pb.G[l]; f.ub = ub(l); f.S = pb.S[l]; f.SR = pb.SR[l]; f.Hp = Hp;
+            bk.note_bytes(8 * unit);
             bk.ew(f, R * Hp);
           })
           bk.gemm_nn(pb.SR[l], Hp, c.Wp + c.pl.wfh[l], Hp, c.Wp + c.pl.wb[l] + (int64_t)3 * Hp * Hp, Hp, pb.G[l] + 3 * Hp, 4 * Hp, M, Hp, Hp,
                      false);
           DGMK_GACT_SWITCH(n.gate_act(), ACT, {
             DgmFwd2Fn<CS, ACT> f; f.xs = pb.xs; f.A4 = pb.G[l]; f.ub = ub(l); f.S = pb.S[l]; f.Sn = pb.S[l + 1]; f.Hp = Hp;
+            bk.note_bytes(6 * unit);
             bk.ew(f, R * Hp);
           })
         }
@@ -218,6 +225,7 @@ struct Pipeline {
     const int Hp = n.Hp;
     const int64_t M = pb.M, R = pb.rows;
     float* Gp = c.Gp;
+    const double unit = 4.0 * (double)M * Hp;
     // output layer: grad W_out = UB^T S_L, grad b_out = sum of value-row cotangents
     bk.wcolsum_acc(pb.S[n.L], Hp, Hp, pb.UB, M, Gp + c.pl.g_outw, c.part, c.part_n);
     bk.wcolsum_acc(pb.UB, 4, 4, pb.E, M, Gp + c.pl.g_outb, c.part, c.part_n);
@@ -225,6 +233,7 @@ struct Pipeline {
     float* SBp = rb.SBb;
     {
       OutRevFn f; f.UB = pb.UB; f.outw = c.Wp + c.pl.outw; f.SB = SBn; f.Hp = Hp; f.o = n.o;
+      bk.note_bytes(unit + 16.0 * M);
       bk.ew4(f, M * Hp);
     }
     DGMK_CS_SWITCH(pb.cs, CS, {
@@ -232,6 +241,7 @@ struct Pipeline {
         if (!n.is_dgm()) {
           DGMK_ACT_SWITCH(n.act, ACT, {
             MlpRevFn<CS, ACT> f; f.G = pb.G[l]; f.YB = SBn; f.AB = rb.AB; f.Hp = Hp;
+            bk.note_bytes(3 * unit);
             bk.ew(f, R * Hp);
           })
           // grad W = Abar^T Y_prev, and grad b (row 2 of Abar^T E) in the same pass
@@ -246,7 +256,7 @@ struct Pipeline {
           DGMK_GACT_SWITCH(n.gate_act(), ACT, {
             DgmRev1Fn<CS, ACT> f; f.A4 = pb.G[l]; f.S = pb.S[l]; f.SBn = SBn; f.AB4 = rb.AB; f.SBp = SBp; f.Hp = Hp;
             if (fe) bk.template dgm_rev1_e<CS>(f, pb.xs, R, gub, c.part, c.part_n);
-            else bk.ew(f, R * Hp);
+            else { bk.note_bytes(9 * unit); bk.ew(f, R * Hp); }
           })
           // (s*R)bar = abar_H W_h, then the R-gate adjoint (one kernel on the fused path)
           if (fe) {
@@ -260,6 +270,7 @@ struct Pipeline {
                        Hp, false);
             DGMK_GACT_SWITCH(n.gate_act(), ACT, {
               DgmRev2Fn<CS, ACT> f; f.A4 = pb.G[l]; f.S = pb.S[l]; f.SRB = rb.SRB; f.AB4 = rb.AB; f.SBp = SBp; f.Hp = Hp;
+              bk.note_bytes(6 * unit);
               bk.ew(f, R * Hp);
             })
           }
@@ -275,6 +286,7 @@ struct Pipeline {
       }
       DGMK_ACT_SWITCH(n.in_act(), ACT, {
         InputRevFn<CS, ACT> f; f.inb = inb(); f.S0 = pb.S[0]; f.SB = SBn; f.AB = rb.AB; f.Hp = Hp; f.ldab = Hp;
+        bk.note_bytes(2 * unit + 4.0 * (double)R * Hp);
         bk.ew4(f, R * Hp);
       })
       bk.wcolsum_acc(rb.AB, Hp, Hp, pb.E, M, Gp + c.pl.g_inb, c.part, c.part_n);

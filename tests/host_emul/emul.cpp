@@ -14,6 +14,7 @@ struct HostBackend {
   bool bad_bt = false;
   int64_t hl_stride = 0;
   explicit HostBackend(void*) {}
+  void note_bytes(double) {}
   template <class F> void ew(const F& f, int64_t n) { for (int64_t i = 0; i < n; ++i) f(i); }
   // the four-units-per-thread form of the same functors: exercise it on the host too
   template <class F> void ew4(const F& f, int64_t n) { for (int64_t k = 0; k < n / 4; ++k) f.vec4(k); }

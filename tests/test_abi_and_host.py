@@ -33,9 +33,29 @@ def test_library_exports_every_declared_symbol(cabi):
 
 
 def test_sass_is_sm100a(cabi):
+    """The built library is sm_100a SASS and its contraction kernels are Blackwell-native: tcgen05 MMAs
+    (UTCHMMA), tensor-memory loads / stores (LDTM / STTM), the bulk-copy engine (UBLKCP), tcgen05.commit (UTCBAR)
+    -- the histogram tools/sass_hist.py writes to profiles/r02_sass_histogram.txt."""
     import subprocess
+    import sys
     out = subprocess.run(["cuobjdump", "-lelf", cabi.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_hist
+    h = sass_hist.histogram(cabi.LIB_PATH)
+    tot = {}
+    for c in h.values():
+        for op, n in c.items():
+            tot[op] = tot.get(op, 0) + n
+    for op in ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "UTCBAR", "FFMA2"):
+        assert tot.get(op, 0) > 0, f"no {op} in the library's SASS"
+    for name, c in h.items():
+        if "lane_gemm_kernel" in name or "wgrad_ws_kernel" in name:
+            assert c["UTCHMMA"] >= 12 and c["LDTM"] > 0 and c["UBLKCP"] + c["LDG"] > 0, name
+        if "lane_gemm_kernel" in name:
+            assert c["STTM"] > 0 and c["UBLKCP"] > 0, name     # weights resident in tensor memory, rows by bulk copy
+        if "small_step_kernel" in name:
+            assert c["UBLKCP"] > 0 and c["FFMA"] > 100, name   # weights staged by the bulk-copy engine, FP32 FMA pipe
 
 
 def test_missing_library_fails_loudly(cabi, monkeypatch):
