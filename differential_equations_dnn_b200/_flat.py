@@ -46,6 +46,21 @@ class deferred_forward:
         return False
 
 
+#: flat buffer address -> owning module (weak): how FusedAdam finds the network from `net.parameters()`.
+#: Nothing is attached to the Parameters themselves, so modules pickle / deepcopy like the reference's.
+_OWNERS: "weakref.WeakValueDictionary[int, FlatParamModule]" = weakref.WeakValueDictionary()
+
+
+def owner_of(params):
+    """The FlatParamModule whose parameter list is exactly `params` (None if there is none)."""
+    if not params:
+        return None
+    net = _OWNERS.get(params[0].data_ptr())
+    if net is None or len(net._plist) != len(params) or any(a is not b for a, b in zip(net._plist, params)):
+        return None
+    return net
+
+
 class FlatParamModule(nn.Module):
     """Base of MLP / DGM: flat storage + kernel-backed forward."""
 
@@ -69,14 +84,19 @@ class FlatParamModule(nn.Module):
         params = list(self.parameters())
         flat = torch.cat([p.detach().reshape(-1) for p in params]).contiguous()
         off = 0
-        me = weakref.ref(self)
         for p in params:
             n = p.numel()
             p.data = flat[off:off + n].view(p.shape)
-            p._dgmk_flat = (me, off)
             off += n
         object.__setattr__(self, "_flat", flat)
         object.__setattr__(self, "_plist", params)
+        _OWNERS[flat.data_ptr()] = self
+
+    def __setstate__(self, state):
+        # pickle / torch.save(net) / copy.deepcopy(net) restore the parameters one by one: re-tie them to one
+        # buffer and register the copy
+        super().__setstate__(state)
+        self._flatten()
 
     def _apply(self, fn, recurse=True):
         out = super()._apply(fn, recurse)

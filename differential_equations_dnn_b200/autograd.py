@@ -38,6 +38,22 @@ def _f32c(t):
     return t.contiguous()
 
 
+def _rows_like(t, B, cols, ref, name):
+    """A per-row operand the reference would broadcast -- a Python number, a 0-dim / [1,cols] / [B,1] tensor
+    (`(y0 - y_ic)`, simple_ode.py:62; `net(xbd1) - x_bd1`, heat.py:91-94) -- expanded to the contiguous
+    [B, cols] float32 block the kernels index."""
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t, dtype=torch.float32, device=ref.device)
+    _need_cuda(t)
+    t = _f32c(t)
+    if t.dim() > 2:
+        raise DgmkError(f"{name}: expected a tensor broadcastable to [{B}, {cols}], got {list(t.shape)}")
+    try:
+        return t.expand(B, cols).contiguous()
+    except RuntimeError:
+        raise DgmkError(f"{name}: expected a tensor broadcastable to [{B}, {cols}], got {list(t.shape)}") from None
+
+
 def _split_grads(net, flat_grad):
     """Views of a flat gradient, one per parameter; None for never-used parameters."""
     return tuple(flat_grad[off:off + n].view(p.shape) if live else None
@@ -129,9 +145,9 @@ class _StepFn(Function):
     kernel sequence; backward scales by the incoming cotangent."""
 
     @staticmethod
-    def _run(B_local, launch):
+    def _run(B_local, launch, device):
         from . import parallel
-        return parallel.reduce_step(launch, B_local)  # [P + 1] = grad_theta | loss
+        return parallel.reduce_step(launch, B_local, device)  # [P + 1] = grad_theta | loss
 
     @staticmethod
     def _finish(ctx, net, out):
@@ -152,9 +168,12 @@ class _StepFn(Function):
 class HeatStepFn(_StepFn):
     @staticmethod
     def forward(ctx, net, x, x0, xbd1, xbd2, x_bd1, x_bd2, kappa, *params):
-        a = [_f32c(t) for t in (x, x0, xbd1, xbd2, x_bd1, x_bd2)]
+        _need_cuda(x, x0, xbd1, xbd2)
+        a = [_f32c(t) for t in (x, x0, xbd1, xbd2)]
+        B = a[0].shape[0]
+        a += [_rows_like(x_bd1, B, 1, a[0], "x_bd1"), _rows_like(x_bd2, B, 1, a[0], "x_bd2")]
         out = _StepFn._run(a[0].shape[0], lambda Bg: kernels.heat_step(net.desc, net.flat_theta(), *a, kappa=kappa,
-                                                             B_global=Bg))
+                                                             B_global=Bg), a[0].device)
         ctx.n_inputs = 8
         return _StepFn._finish(ctx, net, out)
 
@@ -162,8 +181,10 @@ class HeatStepFn(_StepFn):
 class OdeStepFn(_StepFn):
     @staticmethod
     def forward(ctx, net, t, t0, y_ic, *params):
-        a = [_f32c(z) for z in (t, t0, y_ic)]
-        out = _StepFn._run(a[0].shape[0], lambda Bg: kernels.ode_step(net.desc, net.flat_theta(), *a, B_global=Bg))
+        _need_cuda(t, t0)
+        a = [_f32c(t), _f32c(t0)]
+        a.append(_rows_like(y_ic, a[0].shape[0], net.desc.output_dim, a[0], "y_ic"))
+        out = _StepFn._run(a[0].shape[0], lambda Bg: kernels.ode_step(net.desc, net.flat_theta(), *a, B_global=Bg), a[0].device)
         ctx.n_inputs = 4
         return _StepFn._finish(ctx, net, out)
 
@@ -171,8 +192,10 @@ class OdeStepFn(_StepFn):
 class FhnStepFn(_StepFn):
     @staticmethod
     def forward(ctx, net, t, t0, y_ic, *params):
-        a = [_f32c(z) for z in (t, t0, y_ic)]
-        out = _StepFn._run(a[0].shape[0], lambda Bg: kernels.fhn_step(net.desc, net.flat_theta(), *a, B_global=Bg))
+        _need_cuda(t, t0)
+        a = [_f32c(t), _f32c(t0)]
+        a.append(_rows_like(y_ic, a[0].shape[0], net.desc.output_dim, a[0], "y_ic"))
+        out = _StepFn._run(a[0].shape[0], lambda Bg: kernels.fhn_step(net.desc, net.flat_theta(), *a, B_global=Bg), a[0].device)
         ctx.n_inputs = 4
         return _StepFn._finish(ctx, net, out)
 
@@ -181,7 +204,7 @@ class FredholmStepFn(_StepFn):
     @staticmethod
     def forward(ctx, net, x, nodes, *params):
         a = [_f32c(z) for z in (x, nodes)]
-        out = _StepFn._run(a[0].shape[0], lambda Bg: kernels.fredholm_step(net.desc, net.flat_theta(), *a, B_global=Bg))
+        out = _StepFn._run(a[0].shape[0], lambda Bg: kernels.fredholm_step(net.desc, net.flat_theta(), *a, B_global=Bg), a[0].device)
         ctx.n_inputs = 3
         return _StepFn._finish(ctx, net, out)
 

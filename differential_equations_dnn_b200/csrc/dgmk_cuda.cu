@@ -479,14 +479,14 @@ struct CudaBackend {
     const int64_t tile = (int64_t)N * Kd;
     const int64_t per_split = tile + (E ? 4 * (int64_t)N : 0);
     int64_t max_splits = part_n / per_split;
-    if (max_splits > 256) max_splits = 256;
+    if (max_splits > 2048) max_splits = 2048;
     if (max_splits < 1) { if (!err) err = "internal: partial buffer too small"; return; }
-    // aim for >= 4 waves of CTAs, at least 1024 rows per split, at most max_splits
+    // one FP32 partial per ~1024 rows (as many as the partial buffer holds): a split's accumulators are plain
+    // FP32 chains over its rows, and 8192-row chains put grad b of MLP(1,1,32) 3e-5 .. 5e-5 from FP64 at 2^20
+    // rows (the reference's own FP32: 5e-7); the partials are added in FP64
     const int BN = (Kd % 128 == 0) ? 128 : (Kd % 64 == 0) ? 64 : 32;
-    const int tiles = (Kd / BN) * ((N + GEMM_BM - 1) / GEMM_BM);
-    int64_t want = ((int64_t)sms * 2 * 4 + tiles - 1) / tiles;
     int64_t by_rows = (M + 1023) / 1024;
-    int64_t splits = want < by_rows ? want : by_rows;
+    int64_t splits = by_rows;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     int64_t rps = ((M + splits - 1) / splits + 31) / 32 * 32;

@@ -25,7 +25,9 @@ struct NetDims {
   DGMK_HD bool is_dgm() const { return kind != KIND_MLP; }
   // activation used by the hidden stack (dgm_net: tanh; neural_networks.DGM: relu)
   DGMK_HD int gate_act() const { return kind == KIND_MLP ? act : (kind == KIND_DGM_LINEAR ? ACT_TANH : ACT_RELU); }
-  DGMK_HD int in_act() const { return gate_act(); }
+  // input layer: the stack's activation, except neural_networks.DGM(func="tanh"), whose x_in is followed by
+  // tanh while its layers stay ReLU (neural_networks.py:145-147,172)
+  DGMK_HD int in_act() const { return kind == KIND_DGM_RAW ? act : gate_act(); }
 };
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -39,7 +41,8 @@ inline bool make_dims(int kind, int d, int o, int H, int L, int act, NetDims* nd
   if (kind != KIND_MLP && L > 8) { *err = "DGM num_layers must be <= 8"; return false; }
   if (act < 0 || act > 3) { *err = "unknown activation"; return false; }
   nd->kind = kind; nd->d = d; nd->o = o; nd->H = H; nd->L = L;
-  nd->act = (kind == KIND_MLP) ? act : (kind == KIND_DGM_LINEAR ? ACT_TANH : ACT_RELU);
+  if (kind == KIND_DGM_RAW && act != ACT_RELU && act != ACT_TANH) { *err = "neural_networks.DGM: func is relu or tanh"; return false; }
+  nd->act = (kind == KIND_DGM_LINEAR) ? ACT_TANH : act;   // DGM_RAW: activation of the INPUT layer only
   nd->Hp = round_up(H, 32);
   nd->NG = (kind == KIND_MLP) ? 1 : 4;
   return true;

@@ -59,9 +59,9 @@ inline int64_t rev_floats_per_row(const NetDims& n, int C) {
   int64_t Hp = n.Hp;
   return (2 * Hp + n.NG * Hp + (n.is_dgm() ? Hp : 0)) * C;
 }
-constexpr int64_t PART_FLOATS_MIN = 1 << 20;
+constexpr int64_t PART_FLOATS_MIN = 1 << 22;   // 16 MB: 2048 partials of a hidden-size-32 layer
 inline int64_t part_floats(const NetDims& n) {
-  // gemm_tn partials: <= 256 splits x [3Hp, Hp]; wcolsum partials: <= 512 blocks x 4 x 4Hp
+  // gemm_tn partials: >= 256 splits x [3Hp, Hp]; wcolsum partials: <= 512 blocks x 4 x 4Hp
   int64_t a = 256LL * (3 * n.Hp * n.Hp + 4 * 3 * n.Hp), b = 512LL * 4 * 4 * n.Hp;
   int64_t m = a > b ? a : b;
   return m > PART_FLOATS_MIN ? m : PART_FLOATS_MIN;

@@ -12,7 +12,7 @@ from ._loop import graphed_loop, print_progress
 from .auxiliary_funs import fn_timer
 from .heat import _device
 from .optim import FusedAdam
-from .simple_ode import _calls
+from .simple_ode import _require_calls
 
 IEXT, ALPHA, BETA, TAU = 0.5, 0.7, 0.8, 2.5  # fitzhugh_nagumo.py:69-70
 
@@ -26,17 +26,8 @@ def dgm_loss_func(y, y0, t, y_ic):
     """mean(r_Y^2) + mean(r_W^2) + mean((y0 - y_ic)^2), r_Y = Y' + Y^3/3 + W - I - Y,
     r_W = W' + (beta W - alpha - Y)/tau (fitzhugh_nagumo.py:53-97; the last mean runs
     over 2B elements)."""
-    call = _calls(y, y0)
-    if call is not None:
-        net, tt, tt0 = call
-        return ag.FhnStepFn.apply(net, tt, tt0, y_ic, *ag.params_of(net))
-    Y, W = y[:, 0:1], y[:, 1:2]
-    ones = torch.ones_like(Y)
-    dY = torch.autograd.grad(Y, t, grad_outputs=ones, create_graph=True, retain_graph=True)[0]
-    dW = torch.autograd.grad(W, t, grad_outputs=ones, create_graph=True, retain_graph=True)[0]
-    Lx = torch.mean((dY + (Y ** 3 / 3.0 + W - IEXT - Y)) ** 2)
-    Ly = torch.mean((dW + (BETA * W - ALPHA - Y) / TAU) ** 2)
-    return Lx + Ly + torch.mean((y0 - y_ic) ** 2)
+    net, tt, tt0 = _require_calls(y, y0)
+    return ag.FhnStepFn.apply(net, tt, tt0, y_ic, *ag.params_of(net))
 
 
 @fn_timer
@@ -46,6 +37,8 @@ def minimize_loss_dgm(net, y_ic, iterations=1000, batch_size=32, lrate=1e-4, sam
     commented-out `30.01 * rand` (:129), the only one that scales past 200 rows.
     `cuda_graph=True` (single GPU): one captured iteration replayed (`_loop.graphed_loop`)."""
     device = _device()
+    parallel.sync_parameters(net)            # data parallel: rank 0's weights everywhere
+    gen = parallel.sampler_generator(device)  # ... and per-rank rows (None on one GPU: the default RNG stream)
     graphed = cuda_graph and not parallel.is_enabled()
     optimizer = FusedAdam(net.parameters(), lr=lrate, capturable=graphed)
     t0 = torch.zeros([batch_size, 1], device=device)
@@ -55,8 +48,8 @@ def minimize_loss_dgm(net, y_ic, iterations=1000, batch_size=32, lrate=1e-4, sam
 
     def sample():
         if sampler == "grid":
-            return T[prob.multinomial(num_samples=batch_size, replacement=False)].reshape(-1, 1)
-        return 30.01 * torch.rand([batch_size, 1], device=device)
+            return T[prob.multinomial(num_samples=batch_size, replacement=False, generator=gen)].reshape(-1, 1)
+        return 30.01 * torch.rand([batch_size, 1], device=device, generator=gen)
 
     if graphed:
         def step():

@@ -20,10 +20,13 @@ def exact_solution(x):
     return 2.0 * np.sin(x)
 
 
-def draw_nodes(x, k):
+def draw_nodes(x, k, generator=None):
     """The k Monte-Carlo node sets, in the order the reference's loop draws them
-    (`pi/2 * rand_like(x)`, fredholm.py:66-67) -> [k, B, 1]."""
-    return torch.stack([np.pi / 2.0 * torch.rand_like(x) for _ in range(k)])
+    (`pi/2 * rand_like(x)`, fredholm.py:66-67) -> [k, B, 1].  `generator`: the per-rank sampler under data
+    parallelism (parallel.sampler_generator); None = torch's default stream, like the reference."""
+    if generator is None:
+        return torch.stack([np.pi / 2.0 * torch.rand_like(x) for _ in range(k)])
+    return torch.stack([np.pi / 2.0 * torch.rand(x.shape, device=x.device, generator=generator) for _ in range(k)])
 
 
 def dgm_loss_func(net, x, k=50, nodes=None):
@@ -32,13 +35,10 @@ def dgm_loss_func(net, x, k=50, nodes=None):
     shards); by default they are drawn here exactly like the reference does."""
     if nodes is None:
         nodes = draw_nodes(x.detach(), k)
-    if isinstance(net, FlatParamModule):
-        return ag.FredholmStepFn.apply(net, x, nodes, *ag.params_of(net))
-    dr = np.pi / (2 * nodes.shape[0])
-    integral = 0.0
-    for t in nodes:
-        integral = integral + torch.sin(x) * torch.cos(t) * net(t)
-    return torch.mean((net(x) - torch.sin(x) - integral * dr) ** 2)
+    if not isinstance(net, FlatParamModule):
+        raise ag.DgmkError("dgm_loss_func needs one of this package's networks: there is no torch-autograd or CPU "
+                           "fallback path")
+    return ag.FredholmStepFn.apply(net, x, nodes, *ag.params_of(net))
 
 
 @fn_timer
@@ -46,11 +46,13 @@ def minimize_loss_dgm(net, y_ic=2.0, iterations=1000, batch_size=32, lrate=1e-4,
     """fredholm.py:77-117 (y_ic is accepted and unused, as there).
     `cuda_graph=True` (single GPU): one captured iteration replayed (`_loop.graphed_loop`)."""
     device = _device()
+    parallel.sync_parameters(net)            # data parallel: rank 0's weights everywhere
+    gen = parallel.sampler_generator(device)  # ... and per-rank rows (None on one GPU: the default RNG stream)
     graphed = cuda_graph and not parallel.is_enabled()
     optimizer = FusedAdam(net.parameters(), lr=lrate, capturable=graphed)
     if graphed:
         def step():
-            t = np.pi / 2.0 * torch.rand([batch_size, 1], device=device)
+            t = np.pi / 2.0 * torch.rand([batch_size, 1], device=device, generator=gen)
             optimizer.zero_grad()
             loss = dgm_loss_func(net, t, k)
             loss.backward()
@@ -61,9 +63,9 @@ def minimize_loss_dgm(net, y_ic=2.0, iterations=1000, batch_size=32, lrate=1e-4,
         return net, train_loss
     losses = []
     for i in range(iterations):
-        t = np.pi / 2.0 * torch.rand([batch_size, 1], device=device)
+        t = np.pi / 2.0 * torch.rand([batch_size, 1], device=device, generator=gen)
         optimizer.zero_grad()
-        loss = dgm_loss_func(net, t, k)
+        loss = dgm_loss_func(net, t, k, nodes=None if gen is None else draw_nodes(t, k, gen))
         loss.backward()
         optimizer.step()
         losses.append(loss.detach())

@@ -32,30 +32,18 @@ def exact_solution(k=1, nodes=10):
 def dgm_loss_func(net, x, x0, xbd1, xbd2, x_bd1, x_bd2):
     """mean[(u_t - k u_xx)^2 + (u(x,0) - sin x)^2 + (u(0,t) - x_bd1)^2 + (u(pi,t) - x_bd2)^2]
     with k = 1 (heat.py:50-95).  Returns a 0-dim tensor; `.backward()` fills `.grad`."""
-    if isinstance(net, FlatParamModule):
-        return ag.HeatStepFn.apply(net, x, x0, xbd1, xbd2, x_bd1, x_bd2, 1.0, *ag.params_of(net))
-    return reference_style_loss(net, x, x0, xbd1, xbd2, x_bd1, x_bd2)
-
-
-def reference_style_loss(net, x, x0, xbd1, xbd2, x_bd1, x_bd2, kappa=1.0):
-    """The same loss written against the module-level seam (nested autograd.grad on
-    `net(x)`); works for any differentiable `net`, and for ours it exercises
-    JetFn/Link0/Link1.  Used by the parity tests of seam S1."""
-    y = net(x)
-    ones = torch.ones_like(y)
-    dy = torch.autograd.grad(y, x, grad_outputs=ones, create_graph=True, retain_graph=True)[0]
-    u_t, u_x = dy[:, 1:2], dy[:, 0:1]
-    u_xx = torch.autograd.grad(u_x, x, grad_outputs=ones, create_graph=True, retain_graph=True)[0][:, 0:1]
-    res = (u_t - kappa * u_xx) ** 2
-    res = res + (net(x0) - torch.sin(x0[:, 0:1])) ** 2
-    res = res + (net(xbd1) - x_bd1) ** 2 + (net(xbd2) - x_bd2) ** 2
-    return res.mean()
+    if not isinstance(net, FlatParamModule):
+        raise ag.DgmkError("dgm_loss_func needs one of this package's networks (neural_networks.MLP / DGM, "
+                           "dgm_net.DGM): there is no torch-autograd or CPU fallback path")
+    return ag.HeatStepFn.apply(net, x, x0, xbd1, xbd2, x_bd1, x_bd2, 1.0, *ag.params_of(net))
 
 
 def _minimize_graphed(net, iterations, batch_size, lrate, warmup=11):
     """The training loop with one captured iteration replayed (`_loop.graphed_loop`): same RNG stream,
     same arithmetic as the eager loop."""
     device = _device()
+    parallel.sync_parameters(net)            # data parallel: rank 0's weights everywhere
+    gen = parallel.sampler_generator(device)  # ... and per-rank rows (None on one GPU: the default RNG stream)
     optimizer = FusedAdam(net.parameters(), lr=lrate, capturable=True)
     t0 = torch.zeros([batch_size, 1], device=device)
     xbd1 = torch.zeros([batch_size, 1], device=device)
@@ -63,8 +51,8 @@ def _minimize_graphed(net, iterations, batch_size, lrate, warmup=11):
     xbd2y = torch.zeros([batch_size, 1], device=device)
 
     def step():
-        x = torch.pi * torch.rand([batch_size, 1], device=device)
-        t = 3.0 * torch.rand([batch_size, 1], device=device)
+        x = torch.pi * torch.rand([batch_size, 1], device=device, generator=gen)
+        t = 3.0 * torch.rand([batch_size, 1], device=device, generator=gen)
         X = torch.cat([x, t], dim=1)
         X0 = torch.cat([x, t0], dim=1)
         X_BD1 = torch.cat([xbd1, t], dim=1)
@@ -86,12 +74,15 @@ def minimize_loss_dgm(net, iterations=1000, batch_size=32, lrate=1e-4, cuda_grap
     defaults, returns (net, train_loss: list[float]).  Differences that do not change
     results: losses stay on the device and are read back once at the end (plus every
     100th for the progress print) instead of a host sync per step (heat.py:143); under
-    `parallel.enable_data_parallel()` each rank draws its own rows and the gradient is
-    all-reduced inside `dgm_loss_func`.  `cuda_graph=True` (single GPU) replays one captured
+    `parallel.enable_data_parallel()` rank 0's weights are broadcast first, each rank draws its own
+    rows from a per-rank generator (`parallel.sampler_generator`) and the gradient is all-reduced
+    inside `dgm_loss_func`.  `cuda_graph=True` (single GPU) replays one captured
     iteration instead of launching it from Python (`_minimize_graphed`)."""
     if cuda_graph and not parallel.is_enabled():
         return _minimize_graphed(net, iterations, batch_size, lrate)
     device = _device()
+    parallel.sync_parameters(net)            # data parallel: rank 0's weights everywhere
+    gen = parallel.sampler_generator(device)  # ... and per-rank rows (None on one GPU: the default RNG stream)
     optimizer = FusedAdam(net.parameters(), lr=lrate)
     t0 = torch.zeros([batch_size, 1], device=device)
     xbd1 = torch.zeros([batch_size, 1], device=device)
@@ -99,8 +90,8 @@ def minimize_loss_dgm(net, iterations=1000, batch_size=32, lrate=1e-4, cuda_grap
     xbd2y = torch.zeros([batch_size, 1], device=device)
     losses = []
     for i in range(iterations):
-        x = torch.pi * torch.rand([batch_size, 1], device=device)
-        t = 3.0 * torch.rand([batch_size, 1], device=device)
+        x = torch.pi * torch.rand([batch_size, 1], device=device, generator=gen)
+        t = 3.0 * torch.rand([batch_size, 1], device=device, generator=gen)
         X = torch.cat([x, t], dim=1)
         X0 = torch.cat([x, t0], dim=1)
         X_BD1 = torch.cat([xbd1, t], dim=1)

@@ -29,6 +29,16 @@ def _dev_f32(*tensors):
             raise DgmkError("dgmk kernels need contiguous float32 tensors")
 
 
+def _expect(t, shape, name):
+    """The kernels index every row of every operand: a shorter or broadcastable companion would be read out of
+    bounds, so shapes are checked here (leading dimension exact, element count exact)."""
+    want = 1
+    for v in shape:
+        want *= v
+    if t.dim() == 0 or t.shape[0] != shape[0] or t.numel() != want:
+        raise DgmkError(f"{name}: expected shape {list(shape)}, got {list(t.shape)}")
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -83,9 +93,16 @@ def param_layout(desc, lib=None):
     return out
 
 
+_WS_BYTES: dict = {}
+
+
 def _step_common(desc, ws_class, theta, B, k, ws):
-    nbytes = workspace_bytes(desc, ws_class, B, k)
     if ws is None:
+        key = (desc.kind, desc.input_dim, desc.output_dim, desc.hidden_size, desc.num_layers, desc.activation,
+               ws_class, B, k)
+        nbytes = _WS_BYTES.get(key)   # the small-batch loops call this every step: one C call per shape, not per step
+        if nbytes is None:
+            nbytes = _WS_BYTES[key] = workspace_bytes(desc, ws_class, B, k)
         ws = get_workspace(theta.device, min(nbytes, WORKSPACE_CAP_BYTES))
     out = torch.empty(theta.numel() + 1, dtype=torch.float32, device=theta.device)
     return ws, out
@@ -95,7 +112,11 @@ def heat_step(desc, theta, x, x0, xbd1, xbd2, x_bd1, x_bd2, kappa=1.0, B_global=
     """heat.py:50-95 + loss.backward(): returns a [P+1] tensor = [grad_theta | loss]."""
     _dev_f32(theta, x, x0, xbd1, xbd2, x_bd1, x_bd2)
     lib = _cabi.load()
-    B = x.shape[0]
+    B, d = x.shape[0], desc.input_dim
+    for t, nm in ((x, "x"), (x0, "x0"), (xbd1, "xbd1"), (xbd2, "xbd2")):
+        _expect(t, (B, d), nm)
+    _expect(x_bd1, (B, 1), "x_bd1")
+    _expect(x_bd2, (B, 1), "x_bd2")
     ws, out = _step_common(desc, _cabi.WS_HEAT, theta, B, 0, ws)
     P = theta.numel()
     with torch.cuda.device(theta.device):
@@ -111,6 +132,9 @@ def _ode_like(fn_name, ws_class, desc, theta, t, t0, y_ic, B_global, ws):
     _dev_f32(theta, t, t0, y_ic)
     lib = _cabi.load()
     B = t.shape[0]
+    _expect(t, (B, 1), "t")
+    _expect(t0, (B, 1), "t0")
+    _expect(y_ic, (B, desc.output_dim), "y_ic")
     ws, out = _step_common(desc, ws_class, theta, B, 0, ws)
     P = theta.numel()
     with torch.cuda.device(theta.device):
@@ -136,6 +160,8 @@ def fredholm_step(desc, theta, x, nodes, B_global=None, ws=None):
     _dev_f32(theta, x, nodes)
     lib = _cabi.load()
     B, k = x.shape[0], nodes.shape[0]
+    _expect(x, (B, 1), "x")
+    _expect(nodes, (k, B, 1), "nodes")
     ws, out = _step_common(desc, _cabi.WS_FREDHOLM, theta, B, k, ws)
     P = theta.numel()
     with torch.cuda.device(theta.device):

@@ -48,7 +48,7 @@ class DGM(FlatParamModule):
     """neural_networks.DGM(input_dim, output_dim, hidden_size, num_layers, func).
 
     Faithful to the reference's quirks: the inner layers are ReLU
-    whatever `func` says (:146), and `dgm1` is registered but never evaluated (:145) --
+    whatever `func` says (:146) -- `func` only picks the activation after `x_in` (relu, else tanh) -- and `dgm1` is registered but never evaluated (:145) --
     its 12 tensors never receive a gradient, so Adam never moves them.
     """
 
@@ -56,18 +56,15 @@ class DGM(FlatParamModule):
 
     def __init__(self, input_dim=1, output_dim=1, hidden_size=1, num_layers=1, func="relu"):
         super().__init__()
-        if func != "relu":
-            raise NotImplementedError(
-                "neural_networks.DGM(func!='relu') mixes a tanh input layer with ReLU gates; "
-                "only the shipped func='relu' configuration is implemented")
         self.x_in = nn.Linear(input_dim, hidden_size)
         self.dgm1 = DGMLayer(input_dim, hidden_size, func=func)
         self.layers = nn.ModuleList([DGMLayer(input_dim, hidden_size) for _ in range(num_layers)])
         self.x_out = nn.Linear(hidden_size, output_dim)
         xavier_uniform_(self.x_in.weight)
         xavier_uniform_(self.x_out.weight)
+        # func selects the activation after x_in only: relu, anything else tanh (:153-156)
         self._finish_init(_cabi.KIND_DGM_RAW, input_dim, output_dim, hidden_size, num_layers,
-                          _cabi.ACT_RELU)
+                          _cabi.ACT_RELU if func == "relu" else _cabi.ACT_TANH)
 
 
 class MLP(FlatParamModule):

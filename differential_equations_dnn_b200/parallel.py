@@ -17,18 +17,22 @@ import random
 import torch
 import torch.distributed as dist
 
-_STATE = {"group": None, "enabled": False, "bglobal": {}}
+_STATE = {"group": None, "enabled": False, "bglobal": None}
 
 
-def enable_data_parallel(group=None):
-    """Shard every subsequent fused step over `group` (default: WORLD)."""
+def enable_data_parallel(group=None, global_batch=None):
+    """Shard every subsequent fused step over `group` (default: WORLD).
+
+    `global_batch`: the (fixed) sum of the ranks' local row counts, if the caller knows it -- it is validated once,
+    collectively, by the first step and saves the per-step count all-reduce.  Left None, every step all-reduces
+    its local row count, so shards may be unequal and may change from step to step."""
     if not dist.is_initialized():
         raise RuntimeError("torch.distributed is not initialised")
-    _STATE.update(group=group, enabled=True, bglobal={})
+    _STATE.update(group=group, enabled=True, bglobal=None if global_batch is None else [int(global_batch), False])
 
 
 def disable_data_parallel():
-    _STATE.update(group=None, enabled=False, bglobal={})
+    _STATE.update(group=None, enabled=False, bglobal=None)
 
 
 def is_enabled():
@@ -44,32 +48,68 @@ def rank():
 
 
 def global_batch(B_local, device):
-    """Sum of the ranks' local row counts (cached per local size: shards are static)."""
+    """Sum of the ranks' local row counts.  Never cached per rank: with unequal or changing shards a per-rank cache
+    would let one rank skip the collective another rank issues.  Either every rank all-reduces its count every
+    step, or the caller declared a static global batch (`enable_data_parallel(global_batch=...)`), which every
+    rank checks together on the first step."""
     if not _STATE["enabled"]:
         return B_local
-    Bg = _STATE["bglobal"].get(B_local)
-    if Bg is None:
-        t = torch.tensor([B_local], dtype=torch.int64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_STATE["group"])
-        Bg = int(t.item())
-        _STATE["bglobal"][B_local] = Bg
+    declared = _STATE["bglobal"]
+    if declared is not None and declared[1]:
+        return declared[0]
+    t = torch.tensor([B_local], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_STATE["group"])
+    Bg = int(t.item())
+    if declared is not None:
+        if Bg != declared[0]:
+            raise RuntimeError(f"enable_data_parallel(global_batch={declared[0]}) but the ranks hold {Bg} rows")
+        declared[1] = True
     return Bg
 
 
-def reduce_step(launch, B_local, device=None):
-    """Run `launch(B_global) -> [P+1] tensor` on this rank's rows and SUM it over ranks.
-
-    `launch` is the fused step (kernels.*_step) in the product and the oracle in the
-    gloo CPU tests; the collective logic is the same."""
+def reduce_step(launch, B_local, device):
+    """Run `launch(B_global) -> [P+1] tensor` on this rank's rows and SUM it over ranks.  `device`: where the row
+    count is all-reduced (the device of the step's tensors)."""
     if not _STATE["enabled"]:
         return launch(None)
-    if device is None:
-        device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() \
-            else torch.device("cpu")
     Bg = global_batch(B_local, device)
     out = launch(Bg)
     dist.all_reduce(out, op=dist.ReduceOp.SUM, group=_STATE["group"])
     return out
+
+
+def sync_parameters(net):
+    """Broadcast rank 0's flat parameter buffer: after this every replica holds identical weights whatever seeds
+    the ranks constructed their networks with (the drivers call it once before the first step; the identical
+    fused Adam update on the all-reduced gradient then keeps the replicas in step)."""
+    if _STATE["enabled"]:
+        dist.broadcast(net.flat_theta(), src=dist.get_global_rank(_STATE["group"], 0) if _STATE["group"] is not None else 0,
+                       group=_STATE["group"])
+    return net
+
+
+def parameters_in_sync(net):
+    """True when every rank holds the same weights (debug check: compares an all-reduced checksum)."""
+    if not _STATE["enabled"]:
+        return True
+    th = net.flat_theta().double()
+    mine = torch.stack([th.sum(), (th * th).sum()])
+    lo, hi = mine.clone(), mine.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=_STATE["group"])
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=_STATE["group"])
+    return bool(torch.equal(lo, hi))
+
+
+def sampler_generator(device, base_seed=None):
+    """The RNG the drivers draw collocation rows from.  Single process: None (torch's default generator, i.e. the
+    reference's RNG stream).  Data parallel: a per-rank `torch.Generator(device)` seeded with base_seed + rank
+    (base_seed defaults to torch.initial_seed()), so that the ranks draw DIFFERENT rows -- with one shared seed
+    every rank would sample the same batch and N GPUs would do N times the work for no extra samples."""
+    if not _STATE["enabled"]:
+        return None
+    gen = torch.Generator(device=device)
+    gen.manual_seed((torch.initial_seed() if base_seed is None else int(base_seed)) + rank())
+    return gen
 
 
 def shard(t, dim=0):

@@ -31,19 +31,25 @@ def _calls(y, y0):
     return None
 
 
+def _require_calls(y, y0):
+    call = _calls(y, y0)
+    if call is None:
+        raise ag.DgmkError("dgm_loss_func(y, y0, t, y_ic): y and y0 must be what net(t), net(t0) of ONE network of "
+                           "this package returned (directly, or recorded under deferred_forward); there is no "
+                           "torch-autograd or CPU fallback path")
+    return call
+
+
 def dgm_loss_func(y, y0, t, y_ic):
     """mean[(y' + y)^2 + (y(0) - y_ic)^2] (simple_ode.py:41-63).
 
     `y`, `y0` are what `net(t)`, `net(t0)` returned.  If they came from one of this
     package's networks (eagerly, or recorded under `deferred_forward`) the fused step
-    kernel computes loss and parameter gradient in one go; any other tensors fall back
-    to the reference formulation on top of autograd."""
-    call = _calls(y, y0)
-    if call is not None:
-        net, tt, tt0 = call
-        return ag.OdeStepFn.apply(net, tt, tt0, y_ic, *ag.params_of(net))
-    dydt = torch.autograd.grad(y, t, grad_outputs=torch.ones_like(y), create_graph=True, retain_graph=True)[0]
-    return torch.mean((dydt + y) ** 2 + (y0 - y_ic) ** 2)
+    kernel computes loss and parameter gradient in one go.  Anything else (tensors of a
+    foreign network, or outputs post-processed before the call) raises DgmkError: the
+    package has no torch-autograd fallback."""
+    net, tt, tt0 = _require_calls(y, y0)
+    return ag.OdeStepFn.apply(net, tt, tt0, y_ic, *ag.params_of(net))
 
 
 @fn_timer
@@ -51,13 +57,15 @@ def minimize_loss_dgm(net, y_ic=2.0, iterations=1000, batch_size=32, lrate=1e-4,
     """simple_ode.py:66-112: t ~ 1.01 U[0,1), Adam(lr); returns (net, list[float]).
     `cuda_graph=True` (single GPU): one captured iteration replayed (`_loop.graphed_loop`)."""
     device = _device()
+    parallel.sync_parameters(net)            # data parallel: rank 0's weights everywhere
+    gen = parallel.sampler_generator(device)  # ... and per-rank rows (None on one GPU: the default RNG stream)
     graphed = cuda_graph and not parallel.is_enabled()
     optimizer = FusedAdam(net.parameters(), lr=lrate, capturable=graphed)
     y_ic = torch.ones([batch_size, 1], device=device) * y_ic
     t0 = torch.zeros([batch_size, 1], device=device)
     if graphed:
         def step():
-            t = 1.01 * torch.rand([batch_size, 1], device=device)
+            t = 1.01 * torch.rand([batch_size, 1], device=device, generator=gen)
             optimizer.zero_grad()
             with deferred_forward(net):
                 y, y0 = net(t), net(t0)
@@ -70,7 +78,7 @@ def minimize_loss_dgm(net, y_ic=2.0, iterations=1000, batch_size=32, lrate=1e-4,
         return net, train_loss
     losses = []
     for i in range(iterations):
-        t = 1.01 * torch.rand([batch_size, 1], device=device)
+        t = 1.01 * torch.rand([batch_size, 1], device=device, generator=gen)
         optimizer.zero_grad()
         with deferred_forward(net):
             y, y0 = net(t), net(t0)

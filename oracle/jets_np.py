@@ -195,7 +195,7 @@ class Net:
                 q = f"layers.{i}."
                 self.gates.append({g: (p[q + "W" + s].T, p[q + "U" + s].T, p[q + "b" + s][0])
                                    for g, s in (("Z", "z"), ("G", "g"), ("R", "r"), ("H", "h"))})
-            self.act = self.gact = ACT_RELU
+            self.gact = ACT_RELU   # self.act (input layer) = func: relu as shipped, or tanh
 
     # gradient accumulation mirrors the canonical view back to the flat layout
     def grad_views(self, g):

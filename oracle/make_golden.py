@@ -53,7 +53,7 @@ def build(ref, spec: rp.NetSpec, seed):
                              num_layers=spec.L)
     else:
         net = ref["nn"].DGM(input_dim=spec.d, output_dim=spec.o, hidden_size=spec.H,
-                            num_layers=spec.L)
+                            num_layers=spec.L, func=inv[spec.act])
     named = list(net.named_parameters())
     ent = spec.entries()
     assert [n for n, _ in named] == [e[0] for e in ent], "layout order mismatch"
@@ -140,6 +140,8 @@ def main():
         "heat_mlp_sigmoid_h50l1": (S(MLP, 2, 1, 50, 1, rp.ACT_SIGMOID), 33),
         "heat_mlp_leaky_h32l2": (S(MLP, 2, 1, 32, 2, rp.ACT_LEAKY), 64),
         "heat_dgmraw_h32l2": (S(DGR, 2, 1, 32, 2, rp.ACT_RELU), 64),
+        # func="tanh": tanh input layer, ReLU gates (neural_networks.py:145-156)
+        "heat_dgmraw_tanh_h32l1": (S(DGR, 2, 1, 32, 1, rp.ACT_TANH), 40),
     }
     for name, (spec, B) in heat_cases.items():
         if ONLY and name not in ONLY:

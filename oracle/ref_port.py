@@ -140,8 +140,9 @@ def net_forward(spec: NetSpec, theta: torch.Tensor, x: torch.Tensor):
             Hh = gate("H_wh", "H_uh", s * R)
             s = (1 - G) * Hh + Z * s
         return s @ p["S_out.weight"].T + p["S_out.bias"]
-    # DGM_RAW: relu everywhere, [in,out] matrices (neural_networks.py:115-126)
-    s = torch.relu(x @ p["x_in.weight"].T + p["x_in.bias"])
+    # DGM_RAW: relu layers, [in,out] matrices (neural_networks.py:115-126); the input layer follows `func`
+    # (relu as shipped, tanh otherwise: neural_networks.py:153-156,172)
+    s = _act(spec.act, x @ p["x_in.weight"].T + p["x_in.bias"])
     for i in range(spec.L):
         q = f"layers.{i}."
         Z = torch.relu(x @ p[q + "Uz"] + s @ p[q + "Wz"] + p[q + "bz"])

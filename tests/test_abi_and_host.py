@@ -140,3 +140,37 @@ def test_search_space_and_trials():
                                    and 1e-4 <= c["lrate"] <= 1e-1 for c in cfgs)
     res = parallel.run_trials(lambda c: c["lrate"], cfgs)
     assert parallel.best_trial(res)["loss"] == min(c["lrate"] for c in cfgs)
+
+
+def test_modules_pickle_deepcopy_and_optimizer_state():
+    """The drop-in modules support what the reference's do: torch.save(net) / pickle / copy.deepcopy (nothing
+    unpicklable hangs on the Parameters), the copy is re-tied to its own flat buffer, FusedAdam accepts its
+    parameters, and the optimizer's state_dict carries the flat moments and the step count."""
+    import copy
+    import io
+    import pickle
+    import torch
+    from differential_equations_dnn_b200 import dgm_net, neural_networks, optim
+    for net in (dgm_net.DGM(2, 1, 16, 2), neural_networks.MLP(1, 2, 8, 1, activation="tanh"),
+                neural_networks.DGM(1, 1, 8, 1, func="tanh")):
+        ref = net.flat_theta().clone()
+        buf = io.BytesIO()
+        torch.save(net, buf)
+        buf.seek(0)
+        for c in (copy.deepcopy(net), pickle.loads(pickle.dumps(net)), torch.load(buf, weights_only=False)):
+            assert torch.equal(c.flat_theta(), ref) and c.flat_theta().data_ptr() != net.flat_theta().data_ptr()
+            with torch.no_grad():
+                c.flat_theta().add_(1.0)        # parameters are views of the copy's own buffer
+            assert all(torch.equal(p.detach().reshape(-1), c.flat_theta()[off:off + n]) for p, off, n, _ in c.param_slices())
+            assert torch.equal(net.flat_theta(), ref)
+            opt = optim.FusedAdam(c.parameters(), lr=1e-3)
+            assert opt.net is c
+        opt = optim.FusedAdam(net.parameters(), lr=1e-3)
+        opt._t, opt._m, opt._v = 7, torch.full_like(ref, 0.5), torch.full_like(ref, 0.25)
+        sd = opt.state_dict()
+        opt2 = optim.FusedAdam(net.parameters(), lr=1e-2)
+        opt2.load_state_dict(sd)
+        assert opt2._t == 7 and torch.equal(opt2._m, opt._m) and torch.equal(opt2._v, opt._v)
+        assert opt2.param_groups[0]["lr"] == 1e-3
+    with pytest.raises(ValueError):
+        optim.FusedAdam(torch.nn.Linear(2, 2).parameters())

@@ -35,7 +35,28 @@ def _worker(rank, world, port, q):
     out = parallel.reduce_step(launch, mine[0].shape[0], device=torch.device("cpu"))
     assert parallel.global_batch(mine[0].shape[0], torch.device("cpu")) == 64
     sh = parallel.shard(torch.arange(10))
-    q.put((rank, out.numpy(), sh.numpy()))
+    # replicas: different construction seeds per rank -> rank 0's weights after sync_parameters; per-rank sampler
+    from differential_equations_dnn_b200 import dgm_net
+    torch.manual_seed(100 + rank)
+    net = dgm_net.DGM(2, 1, 8, 1)
+    assert not parallel.parameters_in_sync(net)
+    parallel.sync_parameters(net)
+    assert parallel.parameters_in_sync(net)
+    torch.manual_seed(5)   # the SAME seed on every rank (what a launcher typically does)
+    gen = parallel.sampler_generator(torch.device("cpu"))
+    draw = torch.rand(4, generator=gen)
+    # a declared static global batch is validated collectively once, then used without a collective
+    parallel.enable_data_parallel(global_batch=64)
+    assert parallel.global_batch(mine[0].shape[0], torch.device("cpu")) == 64
+    assert parallel.global_batch(mine[0].shape[0], torch.device("cpu")) == 64
+    parallel.enable_data_parallel(global_batch=63)
+    try:
+        parallel.global_batch(mine[0].shape[0], torch.device("cpu"))
+        bad = False
+    except RuntimeError:
+        bad = True
+    assert bad
+    q.put((rank, out.numpy(), sh.numpy(), net.flat_theta().numpy().copy(), draw.numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -52,8 +73,10 @@ def test_dp_sum_equals_single_process():
         p.join(timeout=60)
         assert p.exitcode == 0
     g = dict(np.load(os.path.join(ROOT, "tests", "golden", "heat_dgm_h32l1.npz")))
-    for rank, out, sh in res:
+    for rank, out, sh, th, draw in res:
         assert abs(out[-1] - float(g["loss_f64"])) < 1e-12 * abs(float(g["loss_f64"]))
         assert np.linalg.norm(out[:-1] - g["grad_f64"]) / np.linalg.norm(g["grad_f64"]) < 1e-10
     assert np.array_equal(res[0][1], res[1][1])           # every rank holds the same reduced buffer
+    assert np.array_equal(res[0][3], res[1][3])           # sync_parameters: rank 0's weights on every rank
+    assert not np.array_equal(res[0][4], res[1][4])       # per-rank sampler: different rows from one shared seed
     assert list(res[0][2]) == [0, 1, 2, 3, 4] and list(res[1][2]) == [5, 6, 7, 8, 9]

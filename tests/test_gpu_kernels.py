@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden, golden_names, rel
+from conftest import golden, golden_names, grad_groups, rel
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
@@ -46,8 +46,7 @@ def run(K, prob, g, ws=None, Bg=None):
 def check(K, g, loss, grad, tol=TOL):
     assert abs(loss - float(g["loss"])) <= tol * abs(float(g["loss"])), (loss, float(g["loss"]))
     worst = 0.0
-    for off, r, c, live in K.param_layout(desc_of(g)):
-        n = r * max(c, 1)
+    for off, n, live in grad_groups([(off, r * max(c, 1), live) for off, r, c, live in K.param_layout(desc_of(g))]):
         ref, mine = g["grad"][off:off + n], grad[off:off + n]
         assert np.all(np.isfinite(mine))
         if not live:

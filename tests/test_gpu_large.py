@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import rel
+from conftest import grad_groups, rel
 
 pytestmark = pytest.mark.gpu
 
@@ -149,7 +149,7 @@ def _rows(args, lo, hi):
 
 
 def _worst(a, b, layout):
-    return max([rel(a[off:off + n], b[off:off + n]) for off, n, live in layout
+    return max([rel(a[off:off + n], b[off:off + n]) for off, n, live in grad_groups(layout)
                 if live and np.linalg.norm(b[off:off + n]) > 0] + [0.0])
 
 
@@ -162,6 +162,11 @@ def _parity(out, loss_fn, spec, net, args, B, CH, slicer=_rows, tag="", tol=1e-5
     ref_noise = max(_worst(g32, g64, layout), abs(l32 - l64) / abs(l64))
     e32 = max(_worst(out[:-1], g32, layout), abs(out[-1] - l32) / abs(l32))
     print(f"{tag}: vs FP64 oracle {e64:.2e}, vs FP32 oracle {e32:.2e}, FP32 oracle vs FP64 {ref_noise:.2e}")
+    names = [nm for nm, _ in net.named_parameters()]
+    per = [(rel(out[off:off + n], g64[off:off + n]), rel(g32[off:off + n], g64[off:off + n]), nm, n)
+           for (off, n, live), nm in zip(layout, names) if live and np.linalg.norm(g64[off:off + n]) > 0]
+    for e, r, nm, n in sorted(per, reverse=True)[:4]:
+        print(f"    {nm} [{n}]: ours vs FP64 {e:.2e}, FP32 oracle vs FP64 {r:.2e}")
     for off, n, live in layout:
         if not live:
             assert np.all(out[off:off + n] == 0)
