@@ -229,9 +229,33 @@ def test_engines_agree(K, kind, prob):
         net = neural_networks.MLP(1, 1, 128, 2, activation="sigmoid").cuda()
         host = [1.01 * torch.rand([B, 1], generator=gen), torch.zeros(B, 1), 2.0 * torch.ones(B, 1)]
         fn, ofn = K.ode_step, jets_np.ode_step
-    args = [a.cuda() for a in host]
     d = net.desc
     spec = np.array([d.kind, d.input_dim, d.output_dim, d.hidden_size, d.num_layers, d.activation])
+    if kind == "dgmraw":
+        # ReLU gates (neural_networks.DGM): a pre-activation within FP32 rounding of 0 lands on the other side of
+        # the kink in FP32 than in FP64 and flips that row's derivative -- for ANY FP32 evaluation, the
+        # reference's included, and which rows flip depends on the summation order.  So that the 1e-5 bar
+        # measures arithmetic and not kink lottery, batch rows with a pre-activation closer than 5e-6 to 0 (FP64
+        # oracle; FP32 rounding of these sums is ~1e-7, 3xTF32 ~4e-7) are dropped from the batch (~1 % of rows).
+        npnet = jets_np._net(spec, net.flat_theta().double().cpu().numpy())
+
+        def margin(X):
+            _, st = jets_np.forward(npnet, jets_np.CS_V, X.double().numpy())
+            m = np.abs(st["in"][0][0]).min(1)
+            for L in st["layers"]:
+                for nm in ("aZ", "aG", "aR", "aH"):
+                    m = np.minimum(m, np.abs(L[nm][0]).min(1))
+            return m
+        if prob == "fredholm":
+            m = np.minimum(margin(host[0]), margin(host[1].reshape(-1, 1)).reshape(host[1].shape[0], -1).min(0))
+            keep = torch.from_numpy(m > 5e-6)
+            host = [host[0][keep], host[1][:, keep]]
+        else:
+            m = np.minimum.reduce([margin(h) for h in host[:4]])
+            keep = torch.from_numpy(m > 5e-6)
+            host = [h[keep] for h in host]
+        assert keep.sum().item() > 0.9 * keep.numel(), keep.sum().item()
+    args = [a.contiguous().cuda() for a in host]
     lo, go = ofn(spec, net.flat_theta().double().cpu().numpy(), *[a.double().numpy() for a in host])
     try:
         out = {}
@@ -240,24 +264,9 @@ def test_engines_agree(K, kind, prob):
             out[eng] = fn(d, net.flat_theta(), *args).double().cpu().numpy()
     finally:
         lib.dgmk_set_gemm_engine(1)
-    # ReLU gates (neural_networks.DGM): a pre-activation within FP32 rounding of 0 lands on the other side of
-    # the kink than in FP64 and flips that row's derivative.  The bar is therefore what the reference's own
-    # FP32 arithmetic achieves against FP64 on these inputs (oracle/ref_port in FP32 on this GPU, cuBLAS, TF32
-    # off), measured here: max(1e-5, 2 x that), never more than 1e-4
     tol = TOL
-    if kind == "dgmraw":
-        from oracle import ref_port as rp
-        torch.backends.cuda.matmul.allow_tf32 = False
-        rspec = rp.NetSpec(*[int(v) for v in spec])
-        lfn = rp.fredholm_loss if prob == "fredholm" else rp.heat_loss
-        l32, g32 = rp.loss_and_grad(lfn, rspec, net.flat_theta(), *args)
-        g32 = g32.double().cpu().numpy()
-        worst = max(rel(g32[off:off + n], go[off:off + n]) for (_, off, n, live) in net.param_slices()
-                    if live and np.linalg.norm(go[off:off + n]) > 0)
-        tol = max(TOL, 2 * worst, 2 * abs(float(l32) - lo) / abs(lo))
-        assert tol <= 1e-4, tol
     for eng in (0, 2, 1):
         assert abs(out[eng][-1] - lo) <= tol * abs(lo), (eng, out[eng][-1], lo)
-        for (_, off, n, live) in net.param_slices():
+        for off, n, live in grad_groups([(off, n, live) for _, off, n, live in net.param_slices()]):
             if live and np.linalg.norm(go[off:off + n]) > 0:
                 assert rel(out[eng][off:off + n], go[off:off + n]) < tol, (eng, off, rel(out[eng][off:off + n], go[off:off + n]))

@@ -19,7 +19,7 @@ def build_net(g, seed=1234):
     elif kind == 1:
         net = dgm_net.DGM(d, o, H, L)
     else:
-        net = nn_.DGM(d, o, H, L)
+        net = nn_.DGM(d, o, H, L, func="relu" if act == 0 else "tanh")
     assert np.array_equal(net.flat_theta().numpy(), g["theta"]), "same seed must give the reference's weights"
     return net.cuda()
 
