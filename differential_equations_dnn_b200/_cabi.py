@@ -65,6 +65,7 @@ _CUDA_ONLY = {
     "dgmk_gemm_probe": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int64, _P]),
     "dgmk_gemm_tc_probe": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int64, _P]),
     "dgmk_set_gemm_engine": (None, [C.c_int]),
+    "dgmk_set_tile_engine": (None, [C.c_int]),
     "dgmk_profile": (None, [C.c_int]),
     "dgmk_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double),
                                     C.POINTER(C.c_double)]),
@@ -112,19 +113,27 @@ def make_desc(kind, d, o, H, L, act=ACT_TANH):
 
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared"]
+              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC"]
+SOURCES = ("dgmk_cuda.cu", "dgmk_tile.cu")   # translation units of libdgmk.so, compiled in parallel
 
 
 def build(force=False, verbose=False):
-    """nvcc-compile csrc/dgmk_cuda.cu for sm_100a into csrc/libdgmk.so (in-tree)."""
-    src = os.path.join(CSRC, "dgmk_cuda.cu")
+    """nvcc-compile csrc/*.cu for sm_100a and link them into csrc/libdgmk.so (in-tree)."""
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
     deps.append(os.path.join(CSRC, "..", "..", "include", "dgmk.h"))
     if not force and os.path.exists(LIB_PATH) and all(
             os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
-    cmd = ["nvcc", *NVCC_FLAGS, "-o", LIB_PATH, src]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    subprocess.run(cmd, check=True, cwd=CSRC)
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(CSRC, src[:-3] + ".o")
+        cmd = ["nvcc", *NVCC_FLAGS, "-c", "-o", obj, os.path.join(CSRC, src)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((cmd, subprocess.Popen(cmd, cwd=CSRC)))
+        objs.append(obj)
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, cmd)
+    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH, *objs], check=True, cwd=CSRC)
     return LIB_PATH

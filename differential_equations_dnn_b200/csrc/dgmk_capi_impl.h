@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include "../../include/dgmk.h"
 #include "dgmk_pipeline.h"
+#include "dgmk_steps.h"
 
 namespace dgmk {
 
@@ -123,35 +124,15 @@ struct Api {
     Pipeline<BK> P(bk, c);
     P.pack(theta);
     P.zero_grads();
-    const float inv = (float)(1.0 / (double)Bg);
+    HeatArgs ha; ha.x = x; ha.x0 = x0; ha.xbd1 = xbd1; ha.xbd2 = xbd2; ha.t_bd1 = t_bd1; ha.t_bd2 = t_bd2;
+    ha.kappa = kappa; ha.inv = (float)(1.0 / (double)Bg);
+    if constexpr (BK::kHasTile) {   // hidden sizes <= 64: the whole step in one persistent kernel (dgmk_tile.cuh)
+      if (bk.tile_step(c, DGMK_WS_HEAT, &ha, nullptr, B)) { P.unpack(grad, loss); return finish(bk); }
+    }
     const size_t mark = cv.off;
     for (int64_t p0 = 0; p0 < B; p0 += ch) {
       int64_t r = (B - p0 < ch) ? B - p0 : ch;
-      {  // interior rows: u_t - kappa u_xx  (heat.py:71-87)
-        cv.off = mark;
-        PassBufs pb; RevBufs rb;
-        pb.xs = xsrc1(x + p0 * 2, r, 2);
-        if (!carve_pass(cv, c.n, &pb, r, CS_HEAT) || !carve_rev(cv, c.n, &rb, pb.M)) return fail(DGMK_EWORKSPACE, "workspace too small");
-        P.forward(pb);
-        HeatInteriorFn f; f.U = pb.U; f.UB = pb.UB; f.Lp = c.Lp; f.kappa = kappa; f.inv = inv;
-        bk.ew(f, r);
-        P.add_loss(r);
-        P.reverse(pb, rb);
-      }
-      {  // companions: IC row (x,0), BC rows (0,t) and (pi,t)  (heat.py:89-94)
-        cv.off = mark;
-        PassBufs pb; RevBufs rb;
-        pb.xs.p[0] = x0 + p0 * 2; pb.xs.p[1] = xbd1 + p0 * 2; pb.xs.p[2] = xbd2 + p0 * 2;
-        pb.xs.block_rows = r; pb.xs.block_stride = 0; pb.xs.nptr = 3; pb.xs.d = 2;
-        if (!carve_pass(cv, c.n, &pb, 3 * r, CS_V) || !carve_rev(cv, c.n, &rb, pb.M)) return fail(DGMK_EWORKSPACE, "workspace too small");
-        P.forward(pb);
-        ValueTargetFn f; f.U = pb.U; f.UB = pb.UB; f.Lp = c.Lp; f.xs = pb.xs;
-        f.tgt[0] = nullptr; f.tgt[1] = t_bd1 + p0; f.tgt[2] = t_bd2 + p0;
-        f.mode[0] = 1; f.mode[1] = 0; f.mode[2] = 0; f.o = 1; f.inv = inv;
-        bk.ew(f, 3 * r);
-        P.add_loss(3 * r);
-        P.reverse(pb, rb);
-      }
+      if (!heat_chunk(P, cv, mark, ha, p0, r)) return fail(DGMK_EWORKSPACE, "workspace too small");
     }
     P.unpack(grad, loss);
     return finish(bk);
@@ -174,39 +155,14 @@ struct Api {
     Pipeline<BK> P(bk, c);
     P.pack(theta);
     P.zero_grads();
-    const float inv = (float)(1.0 / (double)Bg);
+    OdeArgs oa; oa.t = t; oa.t0 = t0; oa.y_ic = y_ic; oa.inv = (float)(1.0 / (double)Bg); oa.fhn = fhn ? 1 : 0;
+    if constexpr (BK::kHasTile) {
+      if (bk.tile_step(c, cls, nullptr, &oa, B)) { P.unpack(grad, loss); return finish(bk); }
+    }
     const size_t mark = cv.off;
     for (int64_t p0 = 0; p0 < B; p0 += ch) {
       int64_t r = (B - p0 < ch) ? B - p0 : ch;
-      {
-        cv.off = mark;
-        PassBufs pb; RevBufs rb;
-        pb.xs = xsrc1(t + p0, r, 1);
-        if (!carve_pass(cv, c.n, &pb, r, CS_D1O1) || !carve_rev(cv, c.n, &rb, pb.M)) return fail(DGMK_EWORKSPACE, "workspace too small");
-        P.forward(pb);
-        if (fhn) {
-          FhnInteriorFn f; f.U = pb.U; f.UB = pb.UB; f.Lp = c.Lp; f.I = 0.5f; f.alpha = 0.7f; f.beta = 0.8f; f.tau = 2.5f; f.inv = inv;
-          bk.ew(f, r);
-        } else {
-          OdeInteriorFn f; f.U = pb.U; f.UB = pb.UB; f.Lp = c.Lp; f.inv = inv;
-          bk.ew(f, r);
-        }
-        P.add_loss(r);
-        P.reverse(pb, rb);
-      }
-      {  // initial-condition rows (simple_ode.py:62; fitzhugh_nagumo.py:95 -- mean over 2B elements)
-        cv.off = mark;
-        PassBufs pb; RevBufs rb;
-        pb.xs = xsrc1(t0 + p0, r, 1);
-        if (!carve_pass(cv, c.n, &pb, r, CS_V) || !carve_rev(cv, c.n, &rb, pb.M)) return fail(DGMK_EWORKSPACE, "workspace too small");
-        P.forward(pb);
-        ValueTargetFn f; f.U = pb.U; f.UB = pb.UB; f.Lp = c.Lp; f.xs = pb.xs;
-        f.tgt[0] = y_ic + p0 * c.n.o; f.tgt[1] = f.tgt[2] = nullptr; f.mode[0] = f.mode[1] = f.mode[2] = 0;
-        f.o = c.n.o; f.inv = fhn ? inv * 0.5f : inv;
-        bk.ew(f, r);
-        P.add_loss(r);
-        P.reverse(pb, rb);
-      }
+      if (!ode_like_chunk(P, cv, mark, oa, p0, r)) return fail(DGMK_EWORKSPACE, "workspace too small");
     }
     P.unpack(grad, loss);
     return finish(bk);

@@ -12,6 +12,7 @@
 #include "dgmk_wgrad_ws.cuh"
 #include "dgmk_lane_gemm.cuh"
 #include "dgmk_lane_epi.cuh"
+#include "dgmk_tile.cuh"
 
 namespace dgmk {
 
@@ -24,11 +25,14 @@ static unsigned long long g_launches = 0;
 static bool g_use_tc = true;
 // fused units-on-lanes kernels (GEMM + element-wise stage in one launch) where the shape allows
 static bool g_fuse = true;
+// resident-tile step (one persistent kernel per step) for hidden sizes <= 64 (dgmk_set_tile_engine)
+static bool g_tile = true;
+namespace tk { int launch(int prob, const TileParams& prm, int grid, size_t smem, void* stream); }   // dgmk_tile.cu
 
 // ---- per-kernel-class timing (dgmk_profile*): CUDA events recorded on the launch stream around
 // every launch of a class, with the launch's ALGORITHMIC flops and bytes, so that bench.py can
 // report the roofline of the dominant kernel from the timed region itself ----------------------
-enum { PC_WGRAD = 0, PC_LANE = 1, PC_STREAM_NN = 2, PC_EW = 3, PC_OTHER = 4, PC_COUNT = 5 };
+enum { PC_WGRAD = 0, PC_LANE = 1, PC_STREAM_NN = 2, PC_EW = 3, PC_OTHER = 4, PC_TILE = 5, PC_COUNT = 6 };
 struct ProfClass {
   std::vector<cudaEvent_t> ev;   // begin, end, begin, end, ...
   double flops = 0.0, bytes = 0.0;
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ S
   }
 }
 
-struct CudaBackend {
+struct CudaBackend : BackendTraitsAll {
   cudaStream_t st;
   const char* err;
   int sms;
@@ -583,6 +587,58 @@ struct CudaBackend {
     rowdot_kernel<<<(unsigned)blocks, 256, 0, st>>>(S, lds, W, b, U, M, Hp, o, C);
     post();
   }
+  // ---- resident-tile step (dgmk_tile.cuh): hidden sizes <= 64, the whole step in one persistent kernel --------
+  static constexpr bool kHasTile = true;
+  // Plans the shared-memory layout, launches the kernel on c.Wp (packed) and adds the per-CTA partials into c.Gp.
+  // false = shape not covered (the caller runs the layer-wise path).
+  bool tile_step(Ctx& c, int cls, const HeatArgs* ha, const OdeArgs* oa, int64_t B) {
+    if (!g_tile || c.n.Hp > TILE_MAX_HP || B <= 0) return false;
+    tk::TileParams prm;
+    prm.n = c.n; prm.pl = c.pl; prm.Wp = c.Wp; prm.slots = c.part; prm.B = B;
+    prm.w_floats = (uint32_t)((c.pl.w_total + 3) / 4 * 4);
+    prm.g_floats = (uint32_t)c.pl.g_total;
+    int64_t budget = tk::SMEM_MAX - (int64_t)tk::SCRATCH_FLOATS * 4;
+    prm.w_smem = (int64_t)prm.w_floats * 4 <= 64 * 1024;
+    if (prm.w_smem) budget -= (int64_t)prm.w_floats * 4;
+    prm.g_smem = (int64_t)prm.g_floats * 4 <= 32 * 1024;
+    if (prm.g_smem) budget -= (int64_t)prm.g_floats * 4;
+    // largest tile (points) whose stash + reverse scratch + per-point losses fit
+    auto need = [&](int64_t P) { return (int64_t)chunk_region_bytes(c.n, cls, P, 0) + (loss_points(cls, P, 0) * 4 + 15) / 16 * 16; };
+    int64_t P = 0;
+    const int64_t Pcap = B < 128 ? B : 128;
+    for (int64_t q = 1; q <= Pcap; ++q) { if (need(q) <= budget) P = q; else break; }
+    if (P < 2 && P < B) return false;
+    // spread the points evenly over the tiles of a CTA's share (same tile count, smaller ragged tail)
+    const int64_t nt0 = (B + P - 1) / P;
+    P = (B + nt0 - 1) / nt0;
+    prm.P = (int32_t)P;
+    prm.lp_floats = (uint32_t)((loss_points(cls, P, 0) + 3) / 4 * 4);
+    prm.tile_bytes = (uint32_t)chunk_region_bytes(c.n, cls, P, 0);
+    const int64_t ntiles = (B + P - 1) / P;
+    const int64_t grid = ntiles < sms ? ntiles : sms;
+    const int64_t slots_avail = c.part_n / prm.g_floats;
+    if (slots_avail < grid) return false;
+    int64_t nseg = ((ntiles + grid - 1) / grid + tk::FLUSH_TILES - 1) / tk::FLUSH_TILES;
+    if (nseg * grid > slots_avail) nseg = slots_avail / grid;
+    prm.nslots_per_cta = (int32_t)nseg;
+    if (ha) prm.heat = *ha; else memset(&prm.heat, 0, sizeof(prm.heat));
+    if (oa) prm.ode = *oa; else memset(&prm.ode, 0, sizeof(prm.ode));
+    const size_t smem = (size_t)tk::SCRATCH_FLOATS * 4 + (prm.w_smem ? (size_t)prm.w_floats * 4 : 0) + (prm.g_smem ? (size_t)prm.g_floats * 4 : 0) +
+                        (size_t)prm.lp_floats * 4 + prm.tile_bytes;
+    const size_t slot_bytes = (size_t)grid * nseg * prm.g_floats * 4;
+    note(cudaMemsetAsync(c.part, 0, slot_bytes, st));
+    {
+      // algorithmic flops: 3 M (L c H^2 + 2 H o) per row; algorithmic bytes: the point coordinates
+      const double Mrows = cls == DGMK_WS_HEAT ? 7.0 : 3.0, cc = c.n.is_dgm() ? 8.0 : 2.0;
+      const double falg = 3.0 * Mrows * (c.n.L * cc * c.n.H * c.n.H + 2.0 * c.n.H * c.n.o) * (double)B;
+      const double balg = (cls == DGMK_WS_HEAT ? 40.0 : (cls == DGMK_WS_FHN ? 16.0 : 12.0)) * (double)B;
+      ProfScope ps(PC_TILE, st, falg, balg);
+      note((cudaError_t)tk::launch(cls == DGMK_WS_HEAT ? tk::PROB_HEAT : tk::PROB_ODE, prm, (int)grid, smem, st));
+      ++g_launches;
+    }
+    reduce(c.part, (int)(grid * nseg), prm.g_floats, c.Gp);
+    return !err;
+  }
   void zero(void* p, size_t bytes) { note(cudaMemsetAsync(p, 0, bytes, st)); }
   void copy(void* dst, const void* src, size_t bytes) { note(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st)); }
   bool is_device_ptr(const void* p) {
@@ -626,7 +682,7 @@ unsigned long long dgmk_launch_count(void) { return dgmk::g_launches; }
 // Per-kernel-class timing.  dgmk_profile(1) clears the counters and starts recording CUDA events
 // around every launch; dgmk_profile(0) stops.  dgmk_profile_read(cls, ...) synchronises the
 // recorded events and returns the class's summed duration [ms], launches, algorithmic flops and
-// bytes.  Classes: 0 weight gradient (wgrad_ws), 1 fused units-on-lanes GEMM + element-wise kernels,
+// bytes.  Classes: 5 resident-tile step kernel (hidden sizes <= 64), 0 weight gradient (wgrad_ws), 1 fused units-on-lanes GEMM + element-wise kernels,
 // 2 streaming tcgen05 / FFMA GEMM tiles, 3 stand-alone element-wise kernels, 4 reductions / output layer.
 void dgmk_profile(int on) {
   using namespace dgmk;
@@ -658,6 +714,9 @@ int dgmk_profile_read(int cls, double* ms, long long* launches, double* flops, d
 // 0 = FP32 FFMA2 tiles only; 1 = tcgen05 3xTF32, fused GEMM + element-wise kernels where the shape
 // allows (default); 2 = tcgen05 3xTF32 streaming tiles + separate element-wise kernels
 void dgmk_set_gemm_engine(int engine) { dgmk::g_use_tc = engine != 0; dgmk::g_fuse = engine == 1; }
+// 1 (default) = hidden sizes <= 64 run the resident-tile step (one persistent kernel per step, dgmk_tile.cuh);
+// 0 = the layer-wise path for every hidden size (A/B measurements, tests of the layer-wise path at small sizes)
+void dgmk_set_tile_engine(int on) { dgmk::g_tile = on != 0; }
 // same tcgen05 tile the pipeline launches: C[M,N] = A[M,K] Bt[N,K]^T, lda = ldc = ld
 int dgmk_gemm_tc_probe(const float* A, const float* Bt, float* C, int64_t M, int N, int K, int64_t ld, void* stream) {
   if (N % 128 || K % 32) return DGMK_EINVAL;

@@ -26,8 +26,8 @@ namespace dgmk {
 // ---- workspace carving ----------------------------------------------------------
 struct Carver {
   char* base; size_t off, cap; bool ok;
-  Carver(void* b, size_t c) : base((char*)b), off(0), cap(c), ok(true) {}
-  float* take(int64_t nfloats) {
+  DGMK_HD Carver(void* b, size_t c) : base((char*)b), off(0), cap(c), ok(true) {}
+  DGMK_HD float* take(int64_t nfloats) {
     size_t bytes = ((size_t)nfloats * 4 + 255) / 256 * 256;
     if (off + bytes > cap) { ok = false; return nullptr; }
     float* p = (float*)(base + off);
@@ -35,7 +35,7 @@ struct Carver {
     return p;
   }
 };
-inline size_t carve_bytes(int64_t nfloats) { return ((size_t)nfloats * 4 + 255) / 256 * 256; }
+DGMK_HD size_t carve_bytes(int64_t nfloats) { return ((size_t)nfloats * 4 + 255) / 256 * 256; }
 
 // Buffers of one pass (one set of rows with one channel set)
 struct PassBufs {
@@ -47,7 +47,7 @@ struct PassBufs {
   float* U;            // [M][4] output jets
   float* UB;           // [M][4] output cotangents
 };
-inline int64_t pass_floats_per_row(const NetDims& n, int C) {
+DGMK_HD int64_t pass_floats_per_row(const NetDims& n, int C) {
   // E + states + gates + SR + U + UB (each carved separately; rounding slack added by caller)
   int64_t Hp = n.Hp;
   int64_t f = 4 + (n.L + 1) * Hp + n.L * n.NG * Hp + (n.is_dgm() ? n.L * Hp : 0) + 4 + 4;
@@ -55,15 +55,21 @@ inline int64_t pass_floats_per_row(const NetDims& n, int C) {
 }
 // reverse scratch, shared by all passes of a step (sized for the largest M)
 struct RevBufs { float* SBa; float* SBb; float* AB; float* SRB; };
-inline int64_t rev_floats_per_row(const NetDims& n, int C) {
+DGMK_HD int64_t rev_floats_per_row(const NetDims& n, int C) {
   int64_t Hp = n.Hp;
   return (2 * Hp + n.NG * Hp + (n.is_dgm() ? Hp : 0)) * C;
 }
 constexpr int64_t PART_FLOATS_MIN = 1 << 22;   // 16 MB: 2048 partials of a hidden-size-32 layer
+constexpr int TILE_MAX_HP = 64;          // hidden sizes the resident-tile step covers
+constexpr int64_t TILE_SLOTS = 320;      // per-CTA partial gradient slots it may ask for (>= 2 per SM)
 inline int64_t part_floats(const NetDims& n) {
   // gemm_tn partials: >= 256 splits x [3Hp, Hp]; wcolsum partials: <= 512 blocks x 4 x 4Hp
   int64_t a = 256LL * (3 * n.Hp * n.Hp + 4 * 3 * n.Hp), b = 512LL * 4 * 4 * n.Hp;
   int64_t m = a > b ? a : b;
+  if (n.Hp <= TILE_MAX_HP) {   // resident-tile step: one partial copy of the packed gradient per slot
+    PackedLayout pl; make_packed_layout(n, &pl);
+    if (TILE_SLOTS * pl.g_total > m) m = TILE_SLOTS * pl.g_total;
+  }
   return m > PART_FLOATS_MIN ? m : PART_FLOATS_MIN;
 }
 
@@ -76,7 +82,7 @@ struct Ctx {
   float* Lp;    // per-point loss contributions
 };
 
-inline bool carve_pass(Carver& cv, const NetDims& n, PassBufs* pb, int64_t rows, int cs) {
+DGMK_HD bool carve_pass(Carver& cv, const NetDims& n, PassBufs* pb, int64_t rows, int cs) {
   pb->rows = rows; pb->cs = cs; pb->C = cs_channels(cs); pb->M = rows * pb->C;
   const int64_t M = pb->M, Hp = n.Hp;
   pb->E = cv.take(M * 4);
@@ -89,20 +95,20 @@ inline bool carve_pass(Carver& cv, const NetDims& n, PassBufs* pb, int64_t rows,
   pb->UB = cv.take(M * 4);
   return cv.ok;
 }
-inline size_t pass_bytes(const NetDims& n, int64_t rows, int cs) {
+DGMK_HD size_t pass_bytes(const NetDims& n, int64_t rows, int cs) {
   int64_t C = cs_channels(cs), M = rows * C, Hp = n.Hp;
   size_t b = carve_bytes(M * 4) * 3 + carve_bytes(M * Hp) * (n.L + 1) + carve_bytes(M * n.NG * Hp) * n.L;
   if (n.is_dgm()) b += carve_bytes(M * Hp) * n.L;
   return b;
 }
-inline bool carve_rev(Carver& cv, const NetDims& n, RevBufs* rb, int64_t Mmax) {
+DGMK_HD bool carve_rev(Carver& cv, const NetDims& n, RevBufs* rb, int64_t Mmax) {
   rb->SBa = cv.take(Mmax * n.Hp);
   rb->SBb = cv.take(Mmax * n.Hp);
   rb->AB = cv.take(Mmax * n.NG * n.Hp);
   rb->SRB = n.is_dgm() ? cv.take(Mmax * n.Hp) : nullptr;
   return cv.ok;
 }
-inline size_t rev_bytes(const NetDims& n, int64_t Mmax) {
+DGMK_HD size_t rev_bytes(const NetDims& n, int64_t Mmax) {
   size_t b = carve_bytes(Mmax * n.Hp) * 2 + carve_bytes(Mmax * n.NG * n.Hp);
   if (n.is_dgm()) b += carve_bytes(Mmax * n.Hp);
   return b;
@@ -120,34 +126,61 @@ inline size_t ctx_bytes(const NetDims& n, const PackedLayout& pl, int64_t max_po
 }
 
 // ---- dispatch helpers --------------------------------------------------------------
+// A backend says which channel sets / activations / network families it is compiled for (BackendTraitsAll:
+// everything -- the host-launched backends).  The persistent tile kernels (dgmk_tile.cuh) run this same
+// orchestration INSIDE a kernel, instantiated for exactly the channel sets and activation of one problem, so that
+// the run-time switches below compile to the one live branch.
+struct BackendTraitsAll {
+  static constexpr bool kHasTile = false;   // resident-tile step (dgmk_tile.cuh): CUDA backend only
+  static constexpr bool cs_on(int) { return true; }
+  static constexpr bool act_on(int) { return true; }
+  static constexpr bool mlp_on() { return true; }
+  static constexpr bool dgm_on() { return true; }
+};
+#define DGMK_CS_CASE(id, T, CS, ...) \
+  case id: if constexpr (BK::cs_on(id)) { using CS = T; __VA_ARGS__; } break;
 #define DGMK_CS_SWITCH(cs, CS, ...)                                  \
   switch (cs) {                                                      \
-    case CS_V: { using CS = CsV; __VA_ARGS__; } break;               \
-    case CS_D1O1: { using CS = CsD1O1; __VA_ARGS__; } break;         \
-    case CS_HEAT: { using CS = CsHeat; __VA_ARGS__; } break;         \
-    case CS_D2O1: { using CS = CsD2O1; __VA_ARGS__; } break;         \
-    case CS_D1O2: { using CS = CsD1O2; __VA_ARGS__; } break;         \
-    default: { using CS = CsD2O2; __VA_ARGS__; } break;              \
+    DGMK_CS_CASE(CS_V, CsV, CS, __VA_ARGS__)                         \
+    DGMK_CS_CASE(CS_D1O1, CsD1O1, CS, __VA_ARGS__)                   \
+    DGMK_CS_CASE(CS_HEAT, CsHeat, CS, __VA_ARGS__)                   \
+    DGMK_CS_CASE(CS_D2O1, CsD2O1, CS, __VA_ARGS__)                   \
+    DGMK_CS_CASE(CS_D1O2, CsD1O2, CS, __VA_ARGS__)                   \
+    default: if constexpr (BK::cs_on(CS_D2O2)) { using CS = CsD2O2; __VA_ARGS__; } break; \
   }
+#define DGMK_ACT_CASE(id, ACT, ...) \
+  case id: if constexpr (BK::act_on(id)) { constexpr int ACT = id; __VA_ARGS__; } break;
 #define DGMK_ACT_SWITCH(act, ACT, ...)                                       \
   switch (act) {                                                             \
-    case ACT_RELU: { constexpr int ACT = ACT_RELU; __VA_ARGS__; } break;     \
-    case ACT_SIGMOID: { constexpr int ACT = ACT_SIGMOID; __VA_ARGS__; } break; \
-    case ACT_TANH: { constexpr int ACT = ACT_TANH; __VA_ARGS__; } break;     \
-    default: { constexpr int ACT = ACT_LEAKY; __VA_ARGS__; } break;          \
+    DGMK_ACT_CASE(ACT_RELU, ACT, __VA_ARGS__)                                \
+    DGMK_ACT_CASE(ACT_SIGMOID, ACT, __VA_ARGS__)                             \
+    DGMK_ACT_CASE(ACT_TANH, ACT, __VA_ARGS__)                                \
+    default: if constexpr (BK::act_on(ACT_LEAKY)) { constexpr int ACT = ACT_LEAKY; __VA_ARGS__; } break; \
   }
 // DGM stacks only ever use tanh (dgm_net) or relu (neural_networks.DGM)
-#define DGMK_GACT_SWITCH(act, ACT, ...)                                      \
-  if ((act) == ACT_TANH) { constexpr int ACT = ACT_TANH; __VA_ARGS__; }      \
-  else { constexpr int ACT = ACT_RELU; __VA_ARGS__; }
+#define DGMK_GACT_SWITCH(act, ACT, ...)                                                                   \
+  if ((act) == ACT_TANH) { if constexpr (BK::act_on(ACT_TANH)) { constexpr int ACT = ACT_TANH; __VA_ARGS__; } } \
+  else { if constexpr (BK::act_on(ACT_RELU)) { constexpr int ACT = ACT_RELU; __VA_ARGS__; } }
 
-template <class BK>
+// nvcc: the methods below are __host__ __device__ templates; instantiated for a host-launched backend they
+// call that backend's __host__ methods, which is fine because those instantiations never run on the device
+#if defined(__CUDACC__)
+#define DGMK_NOCHECK _Pragma("nv_exec_check_disable")
+#define DGMK_HD_TEMPLATE DGMK_NOCHECK __host__ __device__
+#define DGMK_HD_PLAIN __host__ __device__
+#else
+#define DGMK_NOCHECK
+#define DGMK_HD_TEMPLATE
+#define DGMK_HD_PLAIN
+#endif
+
+template <class BK, class CX = Ctx>
 struct Pipeline {
-  BK& bk; Ctx& c;
-  Pipeline(BK& b, Ctx& ctx) : bk(b), c(ctx) {}
+  BK& bk; CX& c;
+  DGMK_HD_TEMPLATE Pipeline(BK& b, CX& ctx) : bk(b), c(ctx) {}
 
-  const F4* inb() const { return (const F4*)(c.Wp + c.pl.inb); }
-  const F4* ub(int l) const { return (const F4*)(c.Wp + c.pl.ub[l]); }
+  DGMK_HD const F4* inb() const { return (const F4*)(c.Wp + c.pl.inb); }
+  DGMK_HD const F4* ub(int l) const { return (const F4*)(c.Wp + c.pl.ub[l]); }
 
   void pack(const float* theta) {
     bk.zero(c.Wp, (size_t)c.pl.w_total * 4 * 3);
@@ -164,7 +197,7 @@ struct Pipeline {
   }
 
   // ---------------------------------------------------------------- forward
-  void forward(PassBufs& pb) {
+  DGMK_HD_TEMPLATE void forward(PassBufs& pb) {
     const NetDims& n = c.n;
     const int Hp = n.Hp;
     const int64_t M = pb.M, R = pb.rows;
@@ -179,7 +212,7 @@ struct Pipeline {
         bk.ew4(f, R * Hp);
       })
       for (int l = 0; l < n.L; ++l) {
-        if (!n.is_dgm()) {
+        if (!n.is_dgm()) { if constexpr (BK::mlp_on()) {
           if (bk.lane_ok(Hp, pb.cs)) {   // GEMM + bias + activation in one kernel
             DGMK_ACT_SWITCH(n.act, ACT, {
               bk.template mlp_fwd_fused<CS, ACT>(pb.S[l], pb.G[l], ub(l), pb.S[l + 1], c.Wp + c.pl.wb[l], Hp, M);
@@ -192,7 +225,7 @@ struct Pipeline {
             bk.note_bytes(3 * unit);
             bk.ew(f, R * Hp);
           })
-        } else {
+        } } else if constexpr (BK::dgm_on()) {
           if (bk.lane_ok(Hp, pb.cs)) {   // two kernels per layer: [Z|G|R] + s*R, then H + state update
             DGMK_GACT_SWITCH(n.gate_act(), ACT, {
               bk.template dgm_fwd_fused<CS, ACT>(pb.xs, pb.S[l], pb.G[l], ub(l), pb.SR[l], pb.S[l + 1], c.Wp + c.pl.wb[l], Hp, M);
@@ -220,7 +253,7 @@ struct Pipeline {
 
   // ---------------------------------------------------------------- reverse
   // pb.UB holds the output cotangents; gradients are ACCUMULATED into c.Gp.
-  void reverse(PassBufs& pb, RevBufs& rb) {
+  DGMK_HD_TEMPLATE void reverse(PassBufs& pb, RevBufs& rb) {
     const NetDims& n = c.n;
     const int Hp = n.Hp;
     const int64_t M = pb.M, R = pb.rows;
@@ -238,7 +271,7 @@ struct Pipeline {
     }
     DGMK_CS_SWITCH(pb.cs, CS, {
       for (int l = n.L - 1; l >= 0; --l) {
-        if (!n.is_dgm()) {
+        if (!n.is_dgm()) { if constexpr (BK::mlp_on()) {
           DGMK_ACT_SWITCH(n.act, ACT, {
             MlpRevFn<CS, ACT> f; f.G = pb.G[l]; f.YB = SBn; f.AB = rb.AB; f.Hp = Hp;
             bk.note_bytes(3 * unit);
@@ -248,7 +281,7 @@ struct Pipeline {
           bk.gemm_tn_acc(rb.AB, Hp, pb.S[l], Hp, Gp + c.pl.g_w[l], Hp, Hp, M, pb.E, Gp + c.pl.g_ub[l], Hp, c.part, c.part_n);
           if (bk.lane_ok(Hp, CS_V)) bk.lane_store(rb.AB, Hp, c.Wp + c.pl.wf[l], SBp, Hp, Hp, M);
           else bk.gemm_nn(rb.AB, Hp, c.Wp + c.pl.wb[l], Hp, c.Wp + c.pl.wf[l], Hp, SBp, Hp, M, Hp, Hp, false);
-        } else {
+        } } else if constexpr (BK::dgm_on()) {
           // fused path (hidden size 128): grad[U | b] is formed where the pre-activation cotangents are
           // produced (input_map_adj), so the weight-gradient passes carry no A^T E work
           const bool fe = bk.lane_ok(Hp, pb.cs);
@@ -293,12 +326,12 @@ struct Pipeline {
     })
   }
 
-  void add_loss(int64_t rows) {
+  DGMK_HD_TEMPLATE void add_loss(int64_t rows) {
     bk.wcolsum_acc(c.Lp, 1, 1, nullptr, rows, c.Gp + c.pl.g_acc, c.part, c.part_n);
   }
 };
 
-inline XSrc xsrc1(const float* p, int64_t rows, int d) {
+DGMK_HD XSrc xsrc1(const float* p, int64_t rows, int d) {
   XSrc x; x.p[0] = p; x.p[1] = x.p[2] = nullptr; x.block_rows = rows > 0 ? rows : 1; x.block_stride = 0; x.nptr = 1; x.d = d;
   return x;
 }

@@ -140,10 +140,15 @@ int dgmk_ffma_probe(const float* in, float* out, int blocks, int iters, void* st
  * warp-specialised weight gradient where the shape allows; 2: tcgen05 3xTF32 streaming tiles +
  * separate element-wise kernels */
 void dgmk_set_gemm_engine(int engine);
+/* 1 (default): hidden sizes <= 64 run the resident-tile step -- the whole step (forward jets, loss, reverse,
+ * per-CTA gradient accumulation) in ONE persistent kernel with the activation stash and the packed weights in
+ * shared memory (csrc/dgmk_tile.cuh); 0: the layer-wise path for every hidden size */
+void dgmk_set_tile_engine(int on);
 /* Per-kernel-class timing with CUDA events on the launch stream.  dgmk_profile(1) clears and
  * starts, dgmk_profile(0) stops; dgmk_profile_read synchronises the recorded events and returns the
  * class's summed duration [ms], launches, ALGORITHMIC flops and bytes.  Classes: 0 weight gradient,
- * 1 fused units-on-lanes GEMM + element-wise kernels, 2 streaming GEMM tiles, 3 element-wise. */
+ * 1 fused units-on-lanes GEMM + element-wise kernels, 2 streaming GEMM tiles, 3 element-wise, 4 reductions /
+ * output layer, 5 resident-tile step kernel (hidden sizes <= 64). */
 void dgmk_profile(int on);
 int dgmk_profile_read(int cls, double* ms, long long* launches, double* flops, double* bytes);
 /* Bt holds three [N,K] copies back to back: plain | tf32-hi | tf32-lo */

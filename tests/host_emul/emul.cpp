@@ -10,7 +10,7 @@
 #include "../../differential_equations_dnn_b200/csrc/dgmk_capi_impl.h"
 
 namespace {
-struct HostBackend {
+struct HostBackend : dgmk::BackendTraitsAll {
   bool bad_bt = false;
   int64_t hl_stride = 0;
   explicit HostBackend(void*) {}
