@@ -491,8 +491,9 @@ def main():
              2: "tc::gemm_nn_tc_kernel (streaming tcgen05 tile: K = 3H data gradient; FFMA2 tiles for H % 128 != 0)",
              3: "ew_kernel<...> / rev1_ev_kernel (stand-alone element-wise jet stages, loss, pack, Adam)",
              4: "wcolsum / rowdot / reduce_partials (output layer, column sums, second-stage reductions)",
-             5: "sm::small_step_kernel (hidden size <= 32: whole network resident in shared memory, forward + reverse per "
-                "row tile, FP32 FFMA, register-accumulated weight gradient)"}
+             5: "tk::tile_step_kernel (hidden size <= 64: resident-tile step -- one persistent kernel, a tile of points through "
+                "forward jets, loss and reverse with stash and packed weights in shared memory, FP32 FFMA2, per-CTA "
+                "gradient accumulators)"}
     for cls in range(6):
         t_, n_, f_, b_ = C.c_double(), C.c_longlong(), C.c_double(), C.c_double()
         if lib.dgmk_profile_read(cls, C.byref(t_), C.byref(n_), C.byref(f_), C.byref(b_)) != 0:
@@ -628,7 +629,7 @@ def roofline(lib, wl, prof, B, ms_step, dev):
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr):
             tj = json.load(open(tr))
-            key = {0: "wgrad_ws", 1: "lane_gemm", 2: "gemm_nn_tc", 5: "small_step"}.get(dom)
+            key = {0: "wgrad_ws", 1: "lane_gemm", 2: "gemm_nn_tc", 5: "tile_step"}.get(dom)
             ratio = tj.get(key + "_dram_over_algorithmic") if key else None
             if ratio is not None:   # ncu dram__bytes_read+write per launch / design bytes of that launch
                 roof["traffic"] = ratio * roof["launch"]["design_bytes"]

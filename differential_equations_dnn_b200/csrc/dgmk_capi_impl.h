@@ -35,17 +35,17 @@ inline bool init_ctx(const dgmk_net_desc* d, Ctx* c) {
 }
 
 // bytes of the per-chunk region for `ch` points of a given problem class
-inline size_t chunk_region_bytes(const NetDims& n, int cls, int64_t ch, int k) {
+inline size_t chunk_region_bytes(const NetDims& n, int cls, int64_t ch, int k, bool inplace = false) {
   switch (cls) {
     case DGMK_WS_HEAT: {
-      size_t a = pass_bytes(n, ch, CS_HEAT) + rev_bytes(n, 4 * ch);
-      size_t b = pass_bytes(n, 3 * ch, CS_V) + rev_bytes(n, 3 * ch);
+      size_t a = pass_bytes(n, ch, CS_HEAT) + rev_bytes(n, 4 * ch, inplace);
+      size_t b = pass_bytes(n, 3 * ch, CS_V) + rev_bytes(n, 3 * ch, inplace);
       return a > b ? a : b;
     }
     case DGMK_WS_ODE:
     case DGMK_WS_FHN: {
-      size_t a = pass_bytes(n, ch, CS_D1O1) + rev_bytes(n, 2 * ch);
-      size_t b = pass_bytes(n, ch, CS_V) + rev_bytes(n, ch);
+      size_t a = pass_bytes(n, ch, CS_D1O1) + rev_bytes(n, 2 * ch, inplace);
+      size_t b = pass_bytes(n, ch, CS_V) + rev_bytes(n, ch, inplace);
       return a > b ? a : b;
     }
     case DGMK_WS_FREDHOLM:
@@ -186,6 +186,22 @@ struct Api {
     P.zero_grads();
     const float inv = (float)(1.0 / (double)Bg);
     const float dr = (float)(M_PI / (2.0 * k));
+    FredArgs fa; fa.x = x; fa.nodes = nodes; fa.B = B; fa.k = k; fa.dr = dr; fa.inv = inv;
+    if constexpr (BK::kHasTile) {   // hidden sizes <= 64: blocks of points, node sub-tiles in shared memory (dgmk_tile.cuh)
+      if (bk.tile_step_fredholm(c, fa)) { P.unpack(grad, loss); return finish(bk); }
+    }
+    if (bk.fredholm_block_nodes() > 0) {   // (test harness) the sub-tiled body on the host
+      const int64_t rb_ = bk.fredholm_block_points() < ch ? bk.fredholm_block_points() : ch;
+      float* Ip = cv.take(rb_);
+      if (!Ip) return fail(DGMK_EWORKSPACE, "workspace too small");
+      const size_t markb = cv.off;
+      for (int64_t p0 = 0; p0 < B; p0 += rb_) {
+        int64_t r = (B - p0 < rb_) ? B - p0 : rb_;
+        if (!fredholm_block(P, cv, markb, fa, p0, r, bk.fredholm_block_nodes(), Ip)) return fail(DGMK_EWORKSPACE, "workspace too small");
+      }
+      P.unpack(grad, loss);
+      return finish(bk);
+    }
     const size_t mark = cv.off;
     for (int64_t p0 = 0; p0 < B; p0 += ch) {
       int64_t r = (B - p0 < ch) ? B - p0 : ch;

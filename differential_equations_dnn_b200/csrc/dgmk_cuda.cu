@@ -12,7 +12,7 @@
 #include "dgmk_wgrad_ws.cuh"
 #include "dgmk_lane_gemm.cuh"
 #include "dgmk_lane_epi.cuh"
-#include "dgmk_tile.cuh"
+#include "dgmk_tile_params.h"
 
 namespace dgmk {
 
@@ -26,7 +26,9 @@ static bool g_use_tc = true;
 // fused units-on-lanes kernels (GEMM + element-wise stage in one launch) where the shape allows
 static bool g_fuse = true;
 // resident-tile step (one persistent kernel per step) for hidden sizes <= 64 (dgmk_set_tile_engine)
-static bool g_tile = true;
+static int g_tile = 1;   // 0 off, 1 on where it wins (dispatch rule in tile_step), 2 forced on wherever it fits
+static long long* g_tile_prof = nullptr;   // dgmk_tile_profile: device buffer for CTA 0's stage timeline
+static int g_tile_prof_n = 0;
 namespace tk { int launch(int prob, const TileParams& prm, int grid, size_t smem, void* stream); }   // dgmk_tile.cu
 
 // ---- per-kernel-class timing (dgmk_profile*): CUDA events recorded on the launch stream around
@@ -591,10 +593,9 @@ struct CudaBackend : BackendTraitsAll {
   static constexpr bool kHasTile = true;
   // Plans the shared-memory layout, launches the kernel on c.Wp (packed) and adds the per-CTA partials into c.Gp.
   // false = shape not covered (the caller runs the layer-wise path).
-  bool tile_step(Ctx& c, int cls, const HeatArgs* ha, const OdeArgs* oa, int64_t B) {
-    if (!g_tile || c.n.Hp > TILE_MAX_HP || B <= 0) return false;
-    tk::TileParams prm;
-    prm.n = c.n; prm.pl = c.pl; prm.Wp = c.Wp; prm.slots = c.part; prm.B = B;
+  // shared-memory budget left for the tile region after the fixed parts (scratch, staged weights, accumulators)
+  int64_t tile_fixed(const Ctx& c, tk::TileParams& prm) {
+    prm.n = c.n; prm.pl = c.pl; prm.Wp = c.Wp; prm.slots = c.part;
     prm.w_floats = (uint32_t)((c.pl.w_total + 3) / 4 * 4);
     prm.g_floats = (uint32_t)c.pl.g_total;
     int64_t budget = tk::SMEM_MAX - (int64_t)tk::SCRATCH_FLOATS * 4;
@@ -602,42 +603,91 @@ struct CudaBackend : BackendTraitsAll {
     if (prm.w_smem) budget -= (int64_t)prm.w_floats * 4;
     prm.g_smem = (int64_t)prm.g_floats * 4 <= 32 * 1024;
     if (prm.g_smem) budget -= (int64_t)prm.g_floats * 4;
-    // largest tile (points) whose stash + reverse scratch + per-point losses fit
-    auto need = [&](int64_t P) { return (int64_t)chunk_region_bytes(c.n, cls, P, 0) + (loss_points(cls, P, 0) * 4 + 15) / 16 * 16; };
-    int64_t P = 0;
-    const int64_t Pcap = B < 128 ? B : 128;
-    for (int64_t q = 1; q <= Pcap; ++q) { if (need(q) <= budget) P = q; else break; }
-    if (P < 2 && P < B) return false;
-    // spread the points evenly over the tiles of a CTA's share (same tile count, smaller ragged tail)
-    const int64_t nt0 = (B + P - 1) / P;
-    P = (B + nt0 - 1) / nt0;
-    prm.P = (int32_t)P;
-    prm.lp_floats = (uint32_t)((loss_points(cls, P, 0) + 3) / 4 * 4);
-    prm.tile_bytes = (uint32_t)chunk_region_bytes(c.n, cls, P, 0);
-    const int64_t ntiles = (B + P - 1) / P;
+    prm.lp_floats = prm.coord_floats = prm.ip_floats = 0; prm.J = 0;
+    memset(&prm.heat, 0, sizeof(prm.heat)); memset(&prm.ode, 0, sizeof(prm.ode)); memset(&prm.fred, 0, sizeof(prm.fred));
+    prm.prof = g_tile_prof; prm.prof_n = g_tile_prof_n;
+    return budget;
+  }
+  // grid / slot bookkeeping, launch, second-stage reduction of the per-CTA partials into c.Gp
+  bool tile_launch(Ctx& c, int prob, tk::TileParams& prm, double falg, double balg) {
+    const int64_t ntiles = (prm.B + prm.P - 1) / prm.P;
     const int64_t grid = ntiles < sms ? ntiles : sms;
     const int64_t slots_avail = c.part_n / prm.g_floats;
     if (slots_avail < grid) return false;
     int64_t nseg = ((ntiles + grid - 1) / grid + tk::FLUSH_TILES - 1) / tk::FLUSH_TILES;
     if (nseg * grid > slots_avail) nseg = slots_avail / grid;
     prm.nslots_per_cta = (int32_t)nseg;
-    if (ha) prm.heat = *ha; else memset(&prm.heat, 0, sizeof(prm.heat));
-    if (oa) prm.ode = *oa; else memset(&prm.ode, 0, sizeof(prm.ode));
     const size_t smem = (size_t)tk::SCRATCH_FLOATS * 4 + (prm.w_smem ? (size_t)prm.w_floats * 4 : 0) + (prm.g_smem ? (size_t)prm.g_floats * 4 : 0) +
-                        (size_t)prm.lp_floats * 4 + prm.tile_bytes;
-    const size_t slot_bytes = (size_t)grid * nseg * prm.g_floats * 4;
-    note(cudaMemsetAsync(c.part, 0, slot_bytes, st));
+                        ((size_t)prm.lp_floats + prm.coord_floats + prm.ip_floats) * 4 + prm.tile_bytes;
+    note(cudaMemsetAsync(c.part, 0, (size_t)grid * nseg * prm.g_floats * 4, st));
     {
-      // algorithmic flops: 3 M (L c H^2 + 2 H o) per row; algorithmic bytes: the point coordinates
-      const double Mrows = cls == DGMK_WS_HEAT ? 7.0 : 3.0, cc = c.n.is_dgm() ? 8.0 : 2.0;
-      const double falg = 3.0 * Mrows * (c.n.L * cc * c.n.H * c.n.H + 2.0 * c.n.H * c.n.o) * (double)B;
-      const double balg = (cls == DGMK_WS_HEAT ? 40.0 : (cls == DGMK_WS_FHN ? 16.0 : 12.0)) * (double)B;
       ProfScope ps(PC_TILE, st, falg, balg);
-      note((cudaError_t)tk::launch(cls == DGMK_WS_HEAT ? tk::PROB_HEAT : tk::PROB_ODE, prm, (int)grid, smem, st));
+      note((cudaError_t)tk::launch(prob, prm, (int)grid, smem, st));
       ++g_launches;
     }
     reduce(c.part, (int)(grid * nseg), prm.g_floats, c.Gp);
     return !err;
+  }
+  static int64_t r4(int64_t v) { return (v + 3) / 4 * 4; }
+  // Heat / ODE / FitzHugh-Nagumo.  false = shape not covered or the layer-wise path is faster (the caller runs it).
+  bool tile_step(Ctx& c, int cls, const HeatArgs* ha, const OdeArgs* oa, int64_t B) {
+    if (!g_tile || c.n.Hp > TILE_MAX_HP || B <= 0) return false;
+    tk::TileParams prm;
+    const int64_t budget = tile_fixed(c, prm);
+    prm.B = B;
+    // per-point extras: loss contribution per loss row + the staged coordinates of the larger pass
+    auto coord_fl = [&](int64_t P) { return r4((cls == DGMK_WS_HEAT ? 6 : 1) * P); };
+    auto need = [&](int64_t P) { return (int64_t)chunk_region_bytes(c.n, cls, P, 0, true) + r4(loss_points(cls, P, 0)) * 4 + coord_fl(P) * 4; };
+    int64_t P = 0;
+    const int64_t Pcap = B < 128 ? B : 128;
+    for (int64_t q = 1; q <= Pcap; ++q) { if (need(q) <= budget) P = q; else break; }
+    if (P < 2 && P < B) return false;
+    // Measured crossover (tools/tile_sweep.py): with the whole stash in shared memory the tiles of wide / deep
+    // networks get small (7 heat points at hidden size 64, 3 layers) and past a few thousand rows the layer-wise
+    // path, which streams large GEMMs through HBM, is faster; at hidden size 32 the tile step wins or ties at
+    // every batch size.  g_tile == 2 forces the tile step.
+    const int64_t tile_rows = P * (cls == DGMK_WS_HEAT ? 4 : 2);
+    if (g_tile == 1 && c.n.Hp > 32 && B > 4096 && !(tile_rows >= 48 && B <= 32768)) return false;
+    // spread the points evenly over the tiles (same tile count, smaller ragged tail)
+    const int64_t nt0 = (B + P - 1) / P;
+    P = (B + nt0 - 1) / nt0;
+    prm.P = (int32_t)P;
+    prm.lp_floats = (uint32_t)r4(loss_points(cls, P, 0));
+    prm.coord_floats = (uint32_t)coord_fl(P);
+    prm.tile_bytes = (uint32_t)chunk_region_bytes(c.n, cls, P, 0, true);
+    if (ha) prm.heat = *ha;
+    if (oa) prm.ode = *oa;
+    // algorithmic flops: 3 M (L c H^2 + 2 H o) per row; algorithmic bytes: the point coordinates
+    const double Mrows = cls == DGMK_WS_HEAT ? 7.0 : 3.0, cc = c.n.is_dgm() ? 8.0 : 2.0;
+    const double falg = 3.0 * Mrows * (c.n.L * cc * c.n.H * c.n.H + 2.0 * c.n.H * c.n.o) * (double)B;
+    const double balg = (cls == DGMK_WS_HEAT ? 40.0 : (cls == DGMK_WS_FHN ? 16.0 : 12.0)) * (double)B;
+    return tile_launch(c, cls == DGMK_WS_HEAT ? tk::PROB_HEAT : tk::PROB_ODE, prm, falg, balg);
+  }
+  // Fredholm: a tile is a block of P points with all their k nodes, the node rows taken J nodes at a time
+  bool tile_step_fredholm(Ctx& c, const FredArgs& fa) {
+    if (!g_tile || c.n.Hp > TILE_MAX_HP || fa.B <= 0) return false;
+    tk::TileParams prm;
+    const int64_t budget = tile_fixed(c, prm);
+    prm.B = fa.B;
+    auto need = [&](int64_t P, int64_t J) {
+      return (int64_t)pass_bytes(c.n, P, CS_V) + (int64_t)pass_bytes(c.n, P * J, CS_V) + (int64_t)rev_bytes(c.n, P * J, true) +
+             (r4(P) * 2 + r4(P * J)) * 4;
+    };
+    int64_t P = fa.B < 8 ? fa.B : 8, J = 0;
+    for (int64_t q = 1; q <= fa.k; ++q) { if (need(P, q) <= budget) J = q; else break; }
+    if (J < 1) return false;
+    // measured (tools/tile_prof.py fredholm): 8-point blocks with ~17-node sub-tiles and the second node pass lose to
+    // the layer-wise path's large GEMMs once the step has more than ~64 K node evaluations (k = 1024, B = 2^14:
+    // 66 ms against 46 ms); below that the single launch wins (B = 32, k = 50: 0.30 ms against 1.8 ms)
+    if (g_tile == 1 && fa.B * (int64_t)(fa.k + 1) > 65536) return false;
+    const int64_t nsub = (fa.k + J - 1) / J;   // even sub-tiles
+    J = (fa.k + nsub - 1) / nsub;
+    prm.P = (int32_t)P; prm.J = (int32_t)J;
+    prm.lp_floats = (uint32_t)r4(P); prm.ip_floats = (uint32_t)r4(P); prm.coord_floats = (uint32_t)r4(P * J);
+    prm.tile_bytes = (uint32_t)(pass_bytes(c.n, P, CS_V) + pass_bytes(c.n, P * J, CS_V) + rev_bytes(c.n, P * J, true));
+    prm.fred = fa;
+    const double falg = 3.0 * (fa.k + 1.0) * (c.n.L * (c.n.is_dgm() ? 8.0 : 2.0) * c.n.H * c.n.H + 2.0 * c.n.H * c.n.o) * (double)fa.B;
+    return tile_launch(c, tk::PROB_FRED, prm, falg, 4.0 * (fa.k + 1.0) * (double)fa.B);
   }
   void zero(void* p, size_t bytes) { note(cudaMemsetAsync(p, 0, bytes, st)); }
   void copy(void* dst, const void* src, size_t bytes) { note(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st)); }
@@ -715,8 +765,13 @@ int dgmk_profile_read(int cls, double* ms, long long* launches, double* flops, d
 // allows (default); 2 = tcgen05 3xTF32 streaming tiles + separate element-wise kernels
 void dgmk_set_gemm_engine(int engine) { dgmk::g_use_tc = engine != 0; dgmk::g_fuse = engine == 1; }
 // 1 (default) = hidden sizes <= 64 run the resident-tile step (one persistent kernel per step, dgmk_tile.cuh);
-// 0 = the layer-wise path for every hidden size (A/B measurements, tests of the layer-wise path at small sizes)
-void dgmk_set_tile_engine(int on) { dgmk::g_tile = on != 0; }
+// 0 = the layer-wise path for every hidden size (A/B measurements, tests of the layer-wise path at small sizes);
+// 2 = the resident-tile step wherever a tile fits, whatever the dispatch rule says
+void dgmk_set_tile_engine(int on) { dgmk::g_tile = on; }
+// diagnostic: CTA 0 of the following resident-tile launches writes (clock64, stage kind) pairs -- one per stage, at most
+// n -- into buf (device memory, 2 * n int64); kinds: 0 start, 1 ew, 2 ew4, 3 gemm_nn, 4 column sums, 5 gemm_tn, 6 A^T E,
+// 7 rowdot.  buf = NULL switches it off.
+void dgmk_tile_profile(long long* buf, int n) { dgmk::g_tile_prof = buf; dgmk::g_tile_prof_n = buf ? n : 0; }
 // same tcgen05 tile the pipeline launches: C[M,N] = A[M,K] Bt[N,K]^T, lda = ldc = ld
 int dgmk_gemm_tc_probe(const float* A, const float* Bt, float* C, int64_t M, int N, int K, int64_t ld, void* stream) {
   if (N % 128 || K % 32) return DGMK_EINVAL;

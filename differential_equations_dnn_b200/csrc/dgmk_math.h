@@ -19,6 +19,15 @@
 #define DGMK_HD inline
 #endif
 
+// Inside the resident-tile kernels (dgmk_tile.cu defines DGMK_TILE_TU) every activation / stash buffer a functor
+// touches lives in shared memory: telling the compiler so turns its generic LD / ST (64-bit addresses) into LDS / STS
+// with 32-bit address arithmetic.  A no-op everywhere else (host code, the layer-wise kernels of dgmk_cuda.cu).
+#if defined(DGMK_TILE_TU) && defined(__CUDA_ARCH__)
+#define DGMK_SMEM(p) __builtin_assume(__isShared(p))
+#else
+#define DGMK_SMEM(p) ((void)0)
+#endif
+
 namespace dgmk {
 
 enum { ACT_RELU = 0, ACT_SIGMOID = 1, ACT_TANH = 2, ACT_LEAKY = 3 };

@@ -82,6 +82,7 @@ struct ExtInputFn {
   DGMK_HD void operator()(int64_t p) const {
     const float* x = xs.at(p);
     float* e = E + p * CS::C * 4;
+    DGMK_SMEM(E);
     e[0] = x[0]; e[1] = (xs.d > 1) ? x[1] : 0.f; e[2] = 1.f; e[3] = 0.f;
 #pragma unroll
     for (int c = 1; c < CS::C; ++c) {
@@ -98,6 +99,7 @@ template <class CS, int ACT>
 struct InputFwdFn {
   XSrc xs; const F4* inb; float* S0; int Hp;
   DGMK_HD void operator()(int64_t i) const {
+    DGMK_SMEM(S0);
     int64_t p = idiv(i, Hp); int j = (int)(i - p * Hp);
     const float* x = xs.at(p);
     F4 w = inb[j];
@@ -116,6 +118,7 @@ struct InputFwdFn {
   // four consecutive units of one point (same arithmetic as operator(); 16-byte stores, the point's
   // coordinates and the index division once per four elements); k = p * (Hp/4) + j/4
   DGMK_HD void vec4(int64_t k) const {
+    DGMK_SMEM(S0);
     const int q = Hp >> 2;
     int64_t p = idiv(k, q); int j = (int)(k - p * q) * 4;
     const float* x = xs.at(p);
@@ -145,6 +148,7 @@ template <class CS, int ACT>
 struct InputRevFn {
   const F4* inb; const float* S0; const float* SB; float* AB; int Hp; int64_t ldab;
   DGMK_HD void operator()(int64_t i) const {
+    DGMK_SMEM(S0); DGMK_SMEM(SB); DGMK_SMEM(AB);
     int64_t p = idiv(i, Hp); int j = (int)(i - p * Hp);
     F4 w = inb[j];
     float af[CS::C], yb[CS::C], ab[CS::C];
@@ -160,6 +164,7 @@ struct InputRevFn {
     for (int c = 0; c < CS::C; ++c) AB[(p * CS::C + c) * ldab + j] = ab[c];
   }
   DGMK_HD void vec4(int64_t k) const {   // see InputFwdFn::vec4
+    DGMK_SMEM(S0); DGMK_SMEM(SB); DGMK_SMEM(AB);
     const int q = Hp >> 2;
     int64_t p = idiv(k, q); int j = (int)(k - p * q) * 4;
     const F4 s0 = *reinterpret_cast<const F4*>(S0 + (p * CS::C) * Hp + j);
@@ -193,6 +198,7 @@ template <class CS, int ACT>
 struct MlpActFn {
   float* G; const F4* ub; float* Yn; int Hp;  // G: GEMM output -> a-form in place
   DGMK_HD void operator()(int64_t i) const {
+    DGMK_SMEM(G); DGMK_SMEM(Yn);
     int64_t p = idiv(i, Hp); int j = (int)(i - p * Hp);
     float a[CS::C], y[CS::C];
     float* g = G + (p * CS::C) * Hp + j;
@@ -210,6 +216,7 @@ template <class CS, int ACT>
 struct MlpRevFn {
   const float* G; const float* YB; float* AB; int Hp;
   DGMK_HD void operator()(int64_t i) const {
+    DGMK_SMEM(G); DGMK_SMEM(YB); DGMK_SMEM(AB);
     int64_t p = idiv(i, Hp); int j = (int)(i - p * Hp);
     float af[CS::C], yb[CS::C], ab[CS::C];
     int64_t base = (p * CS::C) * Hp + j;
@@ -245,6 +252,7 @@ template <class CS, int ACT>
 struct DgmFwd1Fn {
   XSrc xs; float* A4; const F4* ub; const float* S; float* SR; int Hp;
   DGMK_HD void operator()(int64_t i) const {
+    DGMK_SMEM(A4); DGMK_SMEM(S); DGMK_SMEM(SR);
     int64_t p = idiv(i, Hp); int j = (int)(i - p * Hp);
     const float* x = xs.at(p);
     const int64_t ld = 4 * (int64_t)Hp;
@@ -275,6 +283,7 @@ template <class CS, int ACT>
 struct DgmFwd2Fn {
   XSrc xs; float* A4; const F4* ub; const float* S; float* Sn; int Hp;
   DGMK_HD void operator()(int64_t i) const {
+    DGMK_SMEM(A4); DGMK_SMEM(S); DGMK_SMEM(Sn);
     int64_t p = idiv(i, Hp); int j = (int)(i - p * Hp);
     const float* x = xs.at(p);
     const int64_t ld = 4 * (int64_t)Hp;
@@ -308,6 +317,7 @@ template <class CS, int ACT>
 struct DgmRev1Fn {
   const float* A4; const float* S; const float* SBn; float* AB4; float* SBp; int Hp;
   DGMK_HD void operator()(int64_t i) const {
+    DGMK_SMEM(A4); DGMK_SMEM(S); DGMK_SMEM(SBn); DGMK_SMEM(AB4); DGMK_SMEM(SBp);
     int64_t p = idiv(i, Hp); int j = (int)(i - p * Hp);
     const int64_t ld = 4 * (int64_t)Hp;
     const float* row = A4 + (p * CS::C) * ld + j;
@@ -408,6 +418,7 @@ template <class CS, int ACT>
 struct DgmRev2Fn {
   const float* A4; const float* S; const float* SRB; float* AB4; float* SBp; int Hp;
   DGMK_HD void operator()(int64_t i) const {
+    DGMK_SMEM(A4); DGMK_SMEM(S); DGMK_SMEM(SRB); DGMK_SMEM(AB4); DGMK_SMEM(SBp);
     int64_t p = idiv(i, Hp); int j = (int)(i - p * Hp);
     const int64_t ld = 4 * (int64_t)Hp;
     const float* row = A4 + (p * CS::C) * ld + 2 * Hp + j;
@@ -434,12 +445,14 @@ struct DgmRev2Fn {
 struct OutRevFn {
   const float* UB; const float* outw; float* SB; int Hp; int o;
   DGMK_HD void operator()(int64_t i) const {
+    DGMK_SMEM(UB); DGMK_SMEM(SB);
     int64_t r = idiv(i, Hp); int j = (int)(i - r * Hp);
     float v = 0.f;
     for (int m = 0; m < o; ++m) v += UB[r * 4 + m] * outw[m * Hp + j];
     SB[i] = v;
   }
   DGMK_HD void vec4(int64_t k) const {   // four consecutive units of row r, same sums
+    DGMK_SMEM(UB); DGMK_SMEM(SB);
     const int q = Hp >> 2;
     int64_t r = idiv(k, q); int j = (int)(k - r * q) * 4;
     const F4 ub = *reinterpret_cast<const F4*>(UB + r * 4);
@@ -461,6 +474,7 @@ struct OutRevFn {
 struct HeatInteriorFn {
   const float* U; float* UB; float* Lp; float kappa, inv;
   DGMK_HD void operator()(int64_t p) const {
+    DGMK_SMEM(U); DGMK_SMEM(UB); DGMK_SMEM(Lp);
     const float* u = U + p * 16;
     float r = u[8] - kappa * u[12];
     float* ub = UB + p * 16;
@@ -476,6 +490,7 @@ struct ValueTargetFn {
   const float* U; float* UB; float* Lp; XSrc xs; const float* tgt[3]; int32_t mode[3];
   int32_t o; float inv;
   DGMK_HD void operator()(int64_t p) const {
+    DGMK_SMEM(U); DGMK_SMEM(UB); DGMK_SMEM(Lp);
     int64_t b = (xs.block_rows >> 31) == 0 ? idiv(p, (int32_t)xs.block_rows) : p / xs.block_rows, w = p - b * xs.block_rows;
     float l = 0.f;
     for (int m = 0; m < 4; ++m) {
@@ -497,6 +512,7 @@ struct ValueTargetFn {
 struct OdeInteriorFn {
   const float* U; float* UB; float* Lp; float inv;
   DGMK_HD void operator()(int64_t p) const {
+    DGMK_SMEM(U); DGMK_SMEM(UB); DGMK_SMEM(Lp);
     const float* u = U + p * 8;
     float r = u[4] + u[0];
     float* ub = UB + p * 8;
@@ -510,6 +526,7 @@ struct OdeInteriorFn {
 struct FhnInteriorFn {
   const float* U; float* UB; float* Lp; float I, alpha, beta, tau, inv;
   DGMK_HD void operator()(int64_t p) const {
+    DGMK_SMEM(U); DGMK_SMEM(UB); DGMK_SMEM(Lp);
     const float* u = U + p * 8;
     float Y = u[0], W = u[1], dY = u[4], dW = u[5];
     float rx = dY + (Y * Y * Y / 3.0f + W - I - Y);
@@ -547,6 +564,49 @@ struct FredholmFn {
       ub[0] = -g * dr * w; ub[1] = 0.f; ub[2] = 0.f; ub[3] = 0.f;
     }
     Lp[p] = r * r * inv;
+  }
+};
+
+// The same loss in three pieces, for the resident-tile step (dgmk_tile.cuh), which walks the k nodes of a block of
+// points in sub-tiles that fit shared memory: FredAccFn adds one sub-tile's terms to the running integral (same
+// j = 0..k-1 order and FP32 arithmetic as FredholmFn), FredResFn forms the residual, the loss and the x-row seed and
+// leaves g = 2 r / B in Ip, FredSeedFn seeds the node rows of one sub-tile.
+struct FredAccFn {
+  const float* Un; const float* x; const float* T; float* Ip; int64_t rows, Tstride; int32_t jj;
+  DGMK_HD void operator()(int64_t p) const {
+    DGMK_SMEM(Un); DGMK_SMEM(Ip);
+    const float sx = sinf(x[p]);
+    float integral = Ip[p];
+    for (int j = 0; j < jj; ++j) {
+      float w = sx * cosf(T[(int64_t)j * Tstride + p]);
+      integral += w * Un[((int64_t)j * rows + p) * 4];
+    }
+    Ip[p] = integral;
+  }
+};
+struct FredResFn {
+  const float* Ux; float* UBx; float* Lp; const float* x; float* Ip; float dr, inv;
+  DGMK_HD void operator()(int64_t p) const {
+    DGMK_SMEM(Ux); DGMK_SMEM(UBx); DGMK_SMEM(Lp); DGMK_SMEM(Ip);
+    const float sx = sinf(x[p]);
+    float integral = Ip[p];
+    integral *= dr;
+    float r = Ux[p * 4] - sx - integral;
+    float g = 2.f * r * inv;
+    UBx[p * 4] = g; UBx[p * 4 + 1] = 0.f; UBx[p * 4 + 2] = 0.f; UBx[p * 4 + 3] = 0.f;
+    Lp[p] = r * r * inv;
+    Ip[p] = g;
+  }
+};
+struct FredSeedFn {
+  float* UBn; const float* x; const float* T; const float* G; int64_t rows, Tstride; float dr;
+  DGMK_HD void operator()(int64_t i) const {
+    DGMK_SMEM(UBn); DGMK_SMEM(G);
+    int64_t j = idiv(i, (int32_t)rows), p = i - j * rows;
+    float w = sinf(x[p]) * cosf(T[j * Tstride + p]);
+    float g = G[p];
+    float* ub = UBn + i * 4;
+    ub[0] = -g * dr * w; ub[1] = 0.f; ub[2] = 0.f; ub[3] = 0.f;
   }
 };
 

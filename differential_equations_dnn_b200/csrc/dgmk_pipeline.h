@@ -101,14 +101,19 @@ DGMK_HD size_t pass_bytes(const NetDims& n, int64_t rows, int cs) {
   if (n.is_dgm()) b += carve_bytes(M * Hp) * n.L;
   return b;
 }
-DGMK_HD bool carve_rev(Carver& cv, const NetDims& n, RevBufs* rb, int64_t Mmax) {
+// inplace (resident-tile step: shared memory is the scarce resource): the reverse pass overwrites the forward
+// stash as it consumes it -- pre-activation cotangents over the a-form gates they are computed from, (s*R)bar over
+// s*R, one state-cotangent buffer instead of a ping-pong pair -- and needs a single [M, Hp] buffer of its own
+DGMK_HD bool carve_rev(Carver& cv, const NetDims& n, RevBufs* rb, int64_t Mmax, bool inplace = false) {
   rb->SBa = cv.take(Mmax * n.Hp);
+  if (inplace) { rb->SBb = rb->SBa; rb->AB = nullptr; rb->SRB = nullptr; return cv.ok; }
   rb->SBb = cv.take(Mmax * n.Hp);
   rb->AB = cv.take(Mmax * n.NG * n.Hp);
   rb->SRB = n.is_dgm() ? cv.take(Mmax * n.Hp) : nullptr;
   return cv.ok;
 }
-DGMK_HD size_t rev_bytes(const NetDims& n, int64_t Mmax) {
+DGMK_HD size_t rev_bytes(const NetDims& n, int64_t Mmax, bool inplace = false) {
+  if (inplace) return carve_bytes(Mmax * n.Hp);
   size_t b = carve_bytes(Mmax * n.Hp) * 2 + carve_bytes(Mmax * n.NG * n.Hp);
   if (n.is_dgm()) b += carve_bytes(Mmax * n.Hp);
   return b;
@@ -132,6 +137,14 @@ inline size_t ctx_bytes(const NetDims& n, const PackedLayout& pl, int64_t max_po
 // the run-time switches below compile to the one live branch.
 struct BackendTraitsAll {
   static constexpr bool kHasTile = false;   // resident-tile step (dgmk_tile.cuh): CUDA backend only
+  DGMK_HD bool inplace_rev() const { return false; }   // reverse pass overwrites the stash (carve_rev)
+  // hook: a backend may copy the `rows` coordinate rows a pass reads to faster memory and re-point xs at the copy
+  DGMK_HD void stage_coords(XSrc&, int64_t) const {}
+  // > 0: the Fredholm step of this backend walks blocks of `fredholm_block_points()` points whose nodes are taken
+  // `fredholm_block_nodes()` at a time (dgmk_steps.h fredholm_block) instead of whole chunks -- the test harness
+  // switches it on to exercise, on the host, the body the resident-tile kernel runs
+  DGMK_HD int fredholm_block_nodes() const { return 0; }
+  DGMK_HD int fredholm_block_points() const { return 0; }
   static constexpr bool cs_on(int) { return true; }
   static constexpr bool act_on(int) { return true; }
   static constexpr bool mlp_on() { return true; }
@@ -262,8 +275,9 @@ struct Pipeline {
     // output layer: grad W_out = UB^T S_L, grad b_out = sum of value-row cotangents
     bk.wcolsum_acc(pb.S[n.L], Hp, Hp, pb.UB, M, Gp + c.pl.g_outw, c.part, c.part_n);
     bk.wcolsum_acc(pb.UB, 4, 4, pb.E, M, Gp + c.pl.g_outb, c.part, c.part_n);
+    const bool ip = bk.inplace_rev();
     float* SBn = rb.SBa;  // cotangent of the current layer's output
-    float* SBp = rb.SBb;
+    float* SBp = rb.SBb;  // (in-place mode: the same buffer -- every stage reads an element before it overwrites it)
     {
       OutRevFn f; f.UB = pb.UB; f.outw = c.Wp + c.pl.outw; f.SB = SBn; f.Hp = Hp; f.o = n.o;
       bk.note_bytes(unit + 16.0 * M);
@@ -271,58 +285,62 @@ struct Pipeline {
     }
     DGMK_CS_SWITCH(pb.cs, CS, {
       for (int l = n.L - 1; l >= 0; --l) {
+        float* AB = ip ? pb.G[l] : rb.AB;      // pre-activation cotangents
         if (!n.is_dgm()) { if constexpr (BK::mlp_on()) {
           DGMK_ACT_SWITCH(n.act, ACT, {
-            MlpRevFn<CS, ACT> f; f.G = pb.G[l]; f.YB = SBn; f.AB = rb.AB; f.Hp = Hp;
+            MlpRevFn<CS, ACT> f; f.G = pb.G[l]; f.YB = SBn; f.AB = AB; f.Hp = Hp;
             bk.note_bytes(3 * unit);
             bk.ew(f, R * Hp);
           })
           // grad W = Abar^T Y_prev, and grad b (row 2 of Abar^T E) in the same pass
-          bk.gemm_tn_acc(rb.AB, Hp, pb.S[l], Hp, Gp + c.pl.g_w[l], Hp, Hp, M, pb.E, Gp + c.pl.g_ub[l], Hp, c.part, c.part_n);
-          if (bk.lane_ok(Hp, CS_V)) bk.lane_store(rb.AB, Hp, c.Wp + c.pl.wf[l], SBp, Hp, Hp, M);
-          else bk.gemm_nn(rb.AB, Hp, c.Wp + c.pl.wb[l], Hp, c.Wp + c.pl.wf[l], Hp, SBp, Hp, M, Hp, Hp, false);
+          bk.gemm_tn_acc(AB, Hp, pb.S[l], Hp, Gp + c.pl.g_w[l], Hp, Hp, M, pb.E, Gp + c.pl.g_ub[l], Hp, c.part, c.part_n);
+          if (bk.lane_ok(Hp, CS_V)) bk.lane_store(AB, Hp, c.Wp + c.pl.wf[l], SBp, Hp, Hp, M);
+          else bk.gemm_nn(AB, Hp, c.Wp + c.pl.wb[l], Hp, c.Wp + c.pl.wf[l], Hp, SBp, Hp, M, Hp, Hp, false);
         } } else if constexpr (BK::dgm_on()) {
           // fused path (hidden size 128): grad[U | b] is formed where the pre-activation cotangents are
           // produced (input_map_adj), so the weight-gradient passes carry no A^T E work
           const bool fe = bk.lane_ok(Hp, pb.cs);
           float* gub = Gp + c.pl.g_ub[l];
+          float* SRB = ip ? pb.SR[l] : rb.SRB;   // (s*R)bar; in place once grad W_h has consumed s*R
+          const float* Ew = fe ? nullptr : pb.E;
           DGMK_GACT_SWITCH(n.gate_act(), ACT, {
-            DgmRev1Fn<CS, ACT> f; f.A4 = pb.G[l]; f.S = pb.S[l]; f.SBn = SBn; f.AB4 = rb.AB; f.SBp = SBp; f.Hp = Hp;
+            DgmRev1Fn<CS, ACT> f; f.A4 = pb.G[l]; f.S = pb.S[l]; f.SBn = SBn; f.AB4 = AB; f.SBp = SBp; f.Hp = Hp;
             if (fe) bk.template dgm_rev1_e<CS>(f, pb.xs, R, gub, c.part, c.part_n);
             else { bk.note_bytes(9 * unit); bk.ew(f, R * Hp); }
           })
+          // grad W_h = abar_H^T (s*R): abar_H is final here, and s*R is dead afterwards
+          bk.gemm_tn_acc(AB + 3 * Hp, 4 * Hp, pb.SR[l], Hp, Gp + c.pl.g_w[l] + (int64_t)3 * Hp * Hp, Hp, Hp, M, Ew, gub + 3 * Hp,
+                         4 * Hp, c.part, c.part_n);
           // (s*R)bar = abar_H W_h, then the R-gate adjoint (one kernel on the fused path)
           if (fe) {
             DGMK_GACT_SWITCH(n.gate_act(), ACT, {
-              bk.template dgm_rev2_fused<CS, ACT>(pb.G[l], pb.S[l], rb.AB, SBp, c.Wp + c.pl.wfh[l], Hp, M);
+              bk.template dgm_rev2_fused<CS, ACT>(pb.G[l], pb.S[l], AB, SBp, c.Wp + c.pl.wfh[l], Hp, M);
             })
             // grad[U_r | b_r] = abar_R^T E: a column-sum pass over abar_R (1 unit)
-            bk.wcolsum_acc(rb.AB + 2 * Hp, 4 * Hp, Hp, pb.E, M, gub + 2 * Hp, c.part, c.part_n, 4 * Hp);
+            bk.wcolsum_acc(AB + 2 * Hp, 4 * Hp, Hp, pb.E, M, gub + 2 * Hp, c.part, c.part_n, 4 * Hp);
           } else {
-            bk.gemm_nn(rb.AB + 3 * Hp, 4 * Hp, c.Wp + c.pl.wb[l] + (int64_t)3 * Hp * Hp, Hp, c.Wp + c.pl.wfh[l], Hp, rb.SRB, Hp, M, Hp,
+            bk.gemm_nn(AB + 3 * Hp, 4 * Hp, c.Wp + c.pl.wb[l] + (int64_t)3 * Hp * Hp, Hp, c.Wp + c.pl.wfh[l], Hp, SRB, Hp, M, Hp,
                        Hp, false);
             DGMK_GACT_SWITCH(n.gate_act(), ACT, {
-              DgmRev2Fn<CS, ACT> f; f.A4 = pb.G[l]; f.S = pb.S[l]; f.SRB = rb.SRB; f.AB4 = rb.AB; f.SBp = SBp; f.Hp = Hp;
+              DgmRev2Fn<CS, ACT> f; f.A4 = pb.G[l]; f.S = pb.S[l]; f.SRB = SRB; f.AB4 = AB; f.SBp = SBp; f.Hp = Hp;
               bk.note_bytes(6 * unit);
               bk.ew(f, R * Hp);
             })
           }
           // s bar += [abar_Z | abar_G | abar_R] [W_z; W_g; W_r]
-          bk.gemm_nn(rb.AB, 4 * Hp, c.Wp + c.pl.wb[l], Hp, c.Wp + c.pl.wf[l], 3 * Hp, SBp, Hp, M, Hp, 3 * Hp, true);
-          // weight gradients; off the fused path grad[U | b] = Abar^T E rides along in the same passes
-          const float* Ew = fe ? nullptr : pb.E;
-          bk.gemm_tn_acc(rb.AB, 4 * Hp, pb.S[l], Hp, Gp + c.pl.g_w[l], 3 * Hp, Hp, M, Ew, gub, 4 * Hp, c.part, c.part_n);
-          bk.gemm_tn_acc(rb.AB + 3 * Hp, 4 * Hp, pb.SR[l], Hp, Gp + c.pl.g_w[l] + (int64_t)3 * Hp * Hp, Hp, Hp, M, Ew, gub + 3 * Hp,
-                         4 * Hp, c.part, c.part_n);
+          bk.gemm_nn(AB, 4 * Hp, c.Wp + c.pl.wb[l], Hp, c.Wp + c.pl.wf[l], 3 * Hp, SBp, Hp, M, Hp, 3 * Hp, true);
+          // weight gradient of the Z, G, R gates; off the fused path grad[U | b] = Abar^T E rides along
+          bk.gemm_tn_acc(AB, 4 * Hp, pb.S[l], Hp, Gp + c.pl.g_w[l], 3 * Hp, Hp, M, Ew, gub, 4 * Hp, c.part, c.part_n);
         }
         float* t = SBn; SBn = SBp; SBp = t;
       }
       DGMK_ACT_SWITCH(n.in_act(), ACT, {
-        InputRevFn<CS, ACT> f; f.inb = inb(); f.S0 = pb.S[0]; f.SB = SBn; f.AB = rb.AB; f.Hp = Hp; f.ldab = Hp;
+        float* ABin = ip ? SBn : rb.AB;
+        InputRevFn<CS, ACT> f; f.inb = inb(); f.S0 = pb.S[0]; f.SB = SBn; f.AB = ABin; f.Hp = Hp; f.ldab = Hp;
         bk.note_bytes(2 * unit + 4.0 * (double)R * Hp);
         bk.ew4(f, R * Hp);
+        bk.wcolsum_acc(ABin, Hp, Hp, pb.E, M, Gp + c.pl.g_inb, c.part, c.part_n);
       })
-      bk.wcolsum_acc(rb.AB, Hp, Hp, pb.E, M, Gp + c.pl.g_inb, c.part, c.part_n);
     })
   }
 

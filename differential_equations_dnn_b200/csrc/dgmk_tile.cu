@@ -2,6 +2,7 @@
 // unit so that the two halves of libdgmk.so compile in parallel; linked into the same library.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC -c dgmk_tile.cu
 #include <atomic>
+#define DGMK_TILE_TU 1   // dgmk_math.h: functor buffers are shared memory in this translation unit
 #include "dgmk_tile.cuh"
 
 namespace dgmk {
@@ -24,7 +25,7 @@ static cudaError_t launch_one(const TileParams& prm, int grid, size_t smem, cuda
 
 template <int PROB>
 static cudaError_t launch_prob(const TileParams& prm, int grid, size_t smem, cudaStream_t st) {
-  constexpr int CSM = (PROB == PROB_HEAT) ? ((1 << CS_HEAT) | (1 << CS_V)) : ((1 << CS_D1O1) | (1 << CS_V));
+  constexpr int CSM = (PROB == PROB_HEAT) ? ((1 << CS_HEAT) | (1 << CS_V)) : (PROB == PROB_ODE ? ((1 << CS_D1O1) | (1 << CS_V)) : (1 << CS_V));
   const NetDims& n = prm.n;
   if (n.kind == KIND_MLP) {
     switch (n.act) {
@@ -43,7 +44,9 @@ static cudaError_t launch_prob(const TileParams& prm, int grid, size_t smem, cud
 // returns a cudaError_t as int
 int launch(int prob, const TileParams& prm, int grid, size_t smem, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  return (int)(prob == PROB_HEAT ? launch_prob<PROB_HEAT>(prm, grid, smem, st) : launch_prob<PROB_ODE>(prm, grid, smem, st));
+  if (prob == PROB_HEAT) return (int)launch_prob<PROB_HEAT>(prm, grid, smem, st);
+  if (prob == PROB_ODE) return (int)launch_prob<PROB_ODE>(prm, grid, smem, st);
+  return (int)launch_prob<PROB_FRED>(prm, grid, smem, st);
 }
 
 }  // namespace tk

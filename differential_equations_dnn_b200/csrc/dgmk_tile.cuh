@@ -14,19 +14,17 @@
 //
 // North star: "a tile of collocation points through every layer, weights held in shared memory ... a matching
 // fused reverse pass accumulates parameter gradients with block reductions".  Reference replaced: heat.py:50-95 +
-// :136-141, simple_ode.py:41-63 + :96-104, fitzhugh_nagumo.py:53-97 + :135-143.
+// :136-141, simple_ode.py:41-63 + :96-104, fitzhugh_nagumo.py:53-97 + :135-143, fredholm.py:47-74 + :104-109 (blocks of
+// points whose k quadrature nodes are walked in sub-tiles: dgmk_steps.h fredholm_block).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "dgmk_steps.h"
+#include "dgmk_tile_params.h"
 
 namespace dgmk {
 namespace tk {
-
-constexpr int NT = 512;                 // threads per CTA (one CTA per SM)
-constexpr int SCRATCH_FLOATS = 4096;    // cross-group reduction scratch (16 KB)
-constexpr int SMEM_MAX = 232448;        // 227 KB opt-in limit per CTA on sm_100
-constexpr int FLUSH_TILES = 256;        // tiles per FP32 accumulation segment
 
 // What Pipeline<> reads of a context; n / pl refer to the kernel's __grid_constant__ parameter block
 struct TileCtx {
@@ -35,9 +33,220 @@ struct TileCtx {
   __device__ TileCtx(const NetDims& n_, const PackedLayout& pl_) : n(n_), pl(pl_), Wp(nullptr), Gp(nullptr), part(nullptr), part_n(0), Lp(nullptr) {}
 };
 
-// CTA-cooperative implementations of the backend primitives.  Every call ends with __syncthreads(): stages are
-// separated exactly like kernel launches on a stream.  CSMASK / ACTMASK / MLP / DGM: the instantiation's live
-// branches of the pipeline's run-time switches (BackendTraitsAll).
+// 16-byte shared-memory accesses by 32-bit address (left to itself ptxas splits a float4 access through a pointer it
+// only ASSUMES to be shared into four scalar LDS)
+__device__ __forceinline__ uint32_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts4(uint32_t a, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// ---- CTA-cooperative stage primitives (free functions, NOT inlined: one copy per translation unit keeps the
+// kernels' instruction footprint and compile time down; every kernel instantiation calls the same code) ---------
+
+// C[M,N] (+)= A[M,K] B[K,N]; A, C in shared memory, B = packed weights (shared memory: BSH, or L2).  TM x 4 register
+// tiles on packed FFMA2, the tile index walks N fastest (a warp shares its A rows by broadcast).
+template <int TM, bool BSH>
+__device__ __noinline__ void gemm_nn_impl(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C,
+                                          int ldc, int M, int N, int K, bool acc) {
+  const uint32_t As = saddr(A), Cs = saddr(C), Bs = BSH ? saddr(B) : 0u;
+  const int ncg = N >> 2, ntiles = ((M + TM - 1) / TM) * ncg;
+  for (int t = threadIdx.x; t < ntiles; t += NT) {
+    const int rg = t / ncg, cg = t - rg * ncg;
+    const int r0 = rg * TM, n0 = cg * 4;
+    uint32_t ar[TM];
+#pragma unroll
+    for (int i = 0; i < TM; ++i) ar[i] = As + (uint32_t)((r0 + i < M ? r0 + i : M - 1) * lda) * 4u;   // clamp: rows >= M are computed, not stored
+    float2 c2[TM][2];
+#pragma unroll
+    for (int i = 0; i < TM; ++i) { c2[i][0] = make_float2(0.f, 0.f); c2[i][1] = make_float2(0.f, 0.f); }
+    uint32_t bs = Bs + (uint32_t)n0 * 4u;
+    const float* bp = B + n0;
+    const uint32_t bstep = (uint32_t)ldb * 4u;
+#pragma unroll 2
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      float4 b4[4];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        if (BSH) { b4[kk] = lds4(bs); bs += bstep; }
+        else b4[kk] = __ldg(reinterpret_cast<const float4*>(bp + (k0 + kk) * ldb));
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        const float4 a4 = lds4(ar[i] + (uint32_t)k0 * 4u);
+        float2 a2;
+        a2 = make_float2(a4.x, a4.x);
+        c2[i][0] = __ffma2_rn(a2, make_float2(b4[0].x, b4[0].y), c2[i][0]); c2[i][1] = __ffma2_rn(a2, make_float2(b4[0].z, b4[0].w), c2[i][1]);
+        a2 = make_float2(a4.y, a4.y);
+        c2[i][0] = __ffma2_rn(a2, make_float2(b4[1].x, b4[1].y), c2[i][0]); c2[i][1] = __ffma2_rn(a2, make_float2(b4[1].z, b4[1].w), c2[i][1]);
+        a2 = make_float2(a4.z, a4.z);
+        c2[i][0] = __ffma2_rn(a2, make_float2(b4[2].x, b4[2].y), c2[i][0]); c2[i][1] = __ffma2_rn(a2, make_float2(b4[2].z, b4[2].w), c2[i][1]);
+        a2 = make_float2(a4.w, a4.w);
+        c2[i][0] = __ffma2_rn(a2, make_float2(b4[3].x, b4[3].y), c2[i][0]); c2[i][1] = __ffma2_rn(a2, make_float2(b4[3].z, b4[3].w), c2[i][1]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      if (r0 + i < M) {
+        const uint32_t p = Cs + (uint32_t)((r0 + i) * ldc + n0) * 4u;
+        float4 v = make_float4(c2[i][0].x, c2[i][0].y, c2[i][1].x, c2[i][1].y);
+        if (acc) { const float4 o = lds4(p); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+        sts4(p, v);
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// column sums with up to four weights per row:
+//   out[(ldo > 0 ? e * ldo : e * N) + n] += sum_r Wt[r][e] * Mat[r * ldm + n]   (e < 4; Wt == nullptr: plain sum, e = 0)
+// thread = (column n, row group g of G = NT / N); groups are combined through the scratch in group order.
+__device__ __noinline__ void wcolsum_impl(const float* __restrict__ Mat_, int ldm, int N, const float* __restrict__ Wt_, int M, float* out,
+                                          bool out_shared, int ldo, float* scratch_) {
+  const float* Mat = Mat_; const float* Wt = Wt_; float* scratch = scratch_;
+  __builtin_assume(__isShared(Mat)); __builtin_assume(__isShared(scratch));
+  if (Wt) __builtin_assume(__isShared(Wt));
+  const int NE = Wt ? 4 : 1;
+  int G = NT / N;
+  if (G * NE * N > SCRATCH_FLOATS) G = SCRATCH_FLOATS / (NE * N);
+  if (G > M) G = M > 0 ? M : 1;
+  const int tid = threadIdx.x, n = tid % N, g = tid / N;
+  if (g < G) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int r = g; r < M; r += G) {
+      const float v = Mat[r * ldm + n];
+      if (Wt) {
+        const float4 w = lds4(saddr(Wt + r * 4));
+        a0 = fmaf(w.x, v, a0); a1 = fmaf(w.y, v, a1); a2 = fmaf(w.z, v, a2); a3 = fmaf(w.w, v, a3);
+      } else {
+        a0 += v;
+      }
+    }
+    float* s = scratch + (g * NE) * N + n;
+    s[0] = a0;
+    if (Wt) { s[N] = a1; s[2 * N] = a2; s[3 * N] = a3; }
+  }
+  __syncthreads();
+  float* outp = out;
+  for (int i = tid; i < NE * N; i += NT) {
+    float t = 0.f;
+    for (int q = 0; q < G; ++q) t += scratch[q * NE * N + i];
+    const int e = i / N, c = i - e * N;
+    outp[(ldo > 0 ? e * ldo : e * N) + c] += t;
+  }
+  __syncthreads();
+}
+
+// out[N, Kd] += A^T S over the tile's M rows.  4 x 4 register tiles over (n, kd); when there are fewer tiles than
+// threads the rows are split over thread groups that are combined through the scratch in group order.
+__device__ __noinline__ void gemm_tn_impl(const float* __restrict__ A_, int lda, const float* __restrict__ S_, int lds, float* out, bool out_shared,
+                                          int N, int Kd, int M, float* scratch_) {
+  float* scratch = scratch_; float* outp = out;
+  __builtin_assume(__isShared(scratch));
+  const uint32_t As = saddr(A_), Ss = saddr(S_);
+  const int nkg = Kd >> 2, ntiles = (N >> 2) * nkg;
+  int G = NT / ntiles;
+  if (G < 1) G = 1;
+  while (G > 1 && (G - 1) * N * Kd > SCRATCH_FLOATS) --G;
+  for (int t0 = 0; t0 < ntiles * G; t0 += NT) {
+    const int t = t0 + threadIdx.x;
+    const int g = t / ntiles, tt = t - g * ntiles;
+    const bool live = t < ntiles * G;
+    const int ng = tt / nkg, kg = tt - ng * nkg;
+    const int n0 = ng * 4, k0 = kg * 4;
+    float2 c2[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { c2[i][0] = make_float2(0.f, 0.f); c2[i][1] = make_float2(0.f, 0.f); }
+    if (live) {
+      uint32_t ap = As + (uint32_t)(g * lda + n0) * 4u, sq = Ss + (uint32_t)(g * lds + k0) * 4u;
+      const uint32_t astep = (uint32_t)(G * lda) * 4u, sstep = (uint32_t)(G * lds) * 4u;
+#pragma unroll 4
+      for (int m = g; m < M; m += G) {
+        const float4 a = lds4(ap);
+        const float4 s = lds4(sq);
+        ap += astep; sq += sstep;
+        const float2 slo = make_float2(s.x, s.y), shi = make_float2(s.z, s.w);
+        float2 a2;
+        a2 = make_float2(a.x, a.x); c2[0][0] = __ffma2_rn(a2, slo, c2[0][0]); c2[0][1] = __ffma2_rn(a2, shi, c2[0][1]);
+        a2 = make_float2(a.y, a.y); c2[1][0] = __ffma2_rn(a2, slo, c2[1][0]); c2[1][1] = __ffma2_rn(a2, shi, c2[1][1]);
+        a2 = make_float2(a.z, a.z); c2[2][0] = __ffma2_rn(a2, slo, c2[2][0]); c2[2][1] = __ffma2_rn(a2, shi, c2[2][1]);
+        a2 = make_float2(a.w, a.w); c2[3][0] = __ffma2_rn(a2, slo, c2[3][0]); c2[3][1] = __ffma2_rn(a2, shi, c2[3][1]);
+      }
+      if (g > 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<float4*>(scratch + (g - 1) * N * Kd + (n0 + i) * Kd + k0) = make_float4(c2[i][0].x, c2[i][0].y, c2[i][1].x, c2[i][1].y);
+      }
+    }
+    if (G > 1) __syncthreads();
+    if (live && g == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 v = make_float4(c2[i][0].x, c2[i][0].y, c2[i][1].x, c2[i][1].y);
+        for (int q = 1; q < G; ++q) {
+          const float4 o = lds4(saddr(scratch + (q - 1) * N * Kd + (n0 + i) * Kd + k0));
+          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        float4* p = reinterpret_cast<float4*>(outp + (n0 + i) * Kd + k0);
+        const float4 o = *p;
+        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        *p = v;
+      }
+    }
+    if (G > 1) __syncthreads();   // (G > 1 implies a single pass of the t0 loop)
+  }
+  __syncthreads();
+}
+
+// u[r][m] = S[r, :] . W[m, :] (+ b[m] on value rows); four lanes per row (a quarter of the units each, starting
+// bank rotated by the row so that the eight rows of a warp hit different banks), combined by shuffles
+__device__ __noinline__ void rowdot_impl(const float* __restrict__ S_, int lds, const float* __restrict__ W, const float* __restrict__ b, float* U_, int M,
+                                         int Hp, int o, int C) {
+  const float* S = S_; float* U = U_;
+  __builtin_assume(__isShared(S)); __builtin_assume(__isShared(U));
+  const int q4 = Hp >> 2;
+  for (int t0 = 0; t0 < 4 * M; t0 += NT) {   // whole warps iterate together (shuffles below)
+    const int t = t0 + threadIdx.x;
+    const int r = t >> 2, part = t & 3;
+    const bool live = r < M;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
+      const float* s = S + r * lds + part * q4;
+      const float* w = W + part * q4;
+      int j = (r >> 3) & (q4 - 1);   // q4 is a power of two (Hp = 32, 64)
+      for (int q = 0; q < q4; ++q) {
+        const float sv = s[j];
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+          if (m < o) acc[m] = fmaf(sv, w[m * Hp + j], acc[m]);
+        j = (j + 1) & (q4 - 1);
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], 1);
+      acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], 2);
+    }
+    if (live && part == 0) {
+      const bool vrow = (r % C) == 0;
+      float4 out;
+      out.x = acc[0] + (vrow ? b[0] : 0.f);
+      out.y = (1 < o) ? acc[1] + (vrow ? b[1] : 0.f) : 0.f;
+      out.z = (2 < o) ? acc[2] + (vrow ? b[2] : 0.f) : 0.f;
+      out.w = (3 < o) ? acc[3] + (vrow ? b[3] : 0.f) : 0.f;
+      sts4(saddr(U + r * 4), out);
+    }
+  }
+  __syncthreads();
+}
+
+// The backend the orchestration templates see.  Every call ends with __syncthreads(): stages are separated exactly
+// like kernel launches on a stream.  CSMASK / ACTMASK / MLP / DGM: the instantiation's live branches of the
+// pipeline's run-time switches (BackendTraitsAll).
 template <int CSMASK, int ACTMASK, bool MLP, bool DGM>
 struct TileBackend {
   static constexpr bool cs_on(int id) { return (CSMASK >> id) & 1; }
@@ -46,6 +255,31 @@ struct TileBackend {
   static constexpr bool dgm_on() { return DGM; }
   float* scratch;   // SCRATCH_FLOATS floats of shared memory
   int64_t hl_stride;
+  bool w_shared, g_shared;   // packed weights / gradient accumulators live in shared memory (else L2)
+  // stage timeline of CTA 0 (dgmk_tile_profile): (clock64, stage kind) after every stage; nullptr = off
+  long long* prof; int prof_i, prof_n;
+  __device__ __forceinline__ void stamp(int kind) {
+    if (prof && threadIdx.x == 0 && prof_i < prof_n) { prof[2 * prof_i] = clock64(); prof[2 * prof_i + 1] = kind; ++prof_i; }
+  }
+  __device__ __forceinline__ bool inplace_rev() const { return true; }   // shared memory is the scarce resource
+  // The coordinates of the tile's rows, copied once per pass from global memory into `coords` (every forward
+  // stage that adds the input map re-reads them: from L2 / HBM that is a ~500-cycle load at the head of a stage
+  // with one or two items per thread).  Rows keep their order; the three companion arrays become one block.
+  float* coords; int coords_cap;
+  __device__ __forceinline__ void stage_coords(XSrc& xs, int64_t rows_) {
+    const int rows = (int)rows_, d = xs.d;
+    if (rows * d > coords_cap) return;
+    for (int i = threadIdx.x; i < rows * d; i += NT) {
+      const int r = i / d, k = i - r * d;
+      coords[i] = __ldg(xs.at(r) + k);
+    }
+    __syncthreads();
+    // same block structure (the loss functors select targets by block), contiguous in the copy
+    const int bd = (int)xs.block_rows * d;
+    xs.p[0] = coords;
+    if (xs.nptr > 1) { xs.p[1] = coords + bd; xs.p[2] = coords + 2 * bd; }
+    else xs.block_stride = bd;
+  }
 
   __device__ __forceinline__ void note_bytes(double) {}
   __device__ __forceinline__ bool lane_ok(int, int) const { return false; }
@@ -64,197 +298,51 @@ struct TileBackend {
   __device__ __forceinline__ void ew(const F& f, int64_t n) {
     for (int i = threadIdx.x; i < (int)n; i += NT) f((int64_t)i);
     __syncthreads();
+    stamp(1);
   }
   template <class F>
   __device__ __forceinline__ void ew4(const F& f, int64_t n) {
     const int n4 = (int)(n >> 2);
     for (int k = threadIdx.x; k < n4; k += NT) f.vec4((int64_t)k);
     __syncthreads();
+    stamp(2);
   }
-
-  // C[M,N] (+)= A[M,K] B[K,N]; A, C in shared memory, B = packed weights (shared memory or L2).  4 x 4 register
-  // tiles on packed FFMA2, the tile index walks N fastest (a warp shares its A rows by broadcast).
-  __device__ void gemm_nn(const float* __restrict__ A, int64_t lda_, const float* __restrict__ B, int64_t ldb_, const float*, int64_t,
-                          float* __restrict__ C, int64_t ldc_, int64_t M_, int N, int K, bool acc) {
-    const int lda = (int)lda_, ldb = (int)ldb_, ldc = (int)ldc_, M = (int)M_;
-    const int ncg = N >> 2, ntiles = ((M + 3) >> 2) * ncg;
-    for (int t = threadIdx.x; t < ntiles; t += NT) {
-      const int rg = t / ncg, cg = t - rg * ncg;
-      const int r0 = rg * 4, n0 = cg * 4;
-      const float* ar[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) ar[i] = A + (r0 + i < M ? r0 + i : M - 1) * lda;   // clamp: rows >= M are computed, not stored
-      float2 c2[4][2];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { c2[i][0] = make_float2(0.f, 0.f); c2[i][1] = make_float2(0.f, 0.f); }
-      const float* bp = B + n0;
-      for (int k0 = 0; k0 < K; k0 += 4) {
-        float4 a4[4], b4[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a4[i] = *reinterpret_cast<const float4*>(ar[i] + k0);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) b4[kk] = *reinterpret_cast<const float4*>(bp + (k0 + kk) * ldb);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const float2 blo = make_float2(b4[kk].x, b4[kk].y), bhi = make_float2(b4[kk].z, b4[kk].w);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float av = kk == 0 ? a4[i].x : (kk == 1 ? a4[i].y : (kk == 2 ? a4[i].z : a4[i].w));
-            const float2 a2 = make_float2(av, av);
-            c2[i][0] = __ffma2_rn(a2, blo, c2[i][0]);
-            c2[i][1] = __ffma2_rn(a2, bhi, c2[i][1]);
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (r0 + i < M) {
-          float4* p = reinterpret_cast<float4*>(C + (r0 + i) * ldc + n0);
-          float4 v = make_float4(c2[i][0].x, c2[i][0].y, c2[i][1].x, c2[i][1].y);
-          if (acc) { const float4 o = *p; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-          *p = v;
-        }
-      }
+  // TM = 8 when 4-row tiles would need more than one round of the CTA's threads
+  __device__ __forceinline__ void gemm_nn(const float* A, int64_t lda, const float* B, int64_t ldb, const float*, int64_t, float* C, int64_t ldc,
+                                          int64_t M_, int N, int K, bool acc) {
+    const int M = (int)M_;
+    const bool big = ((M + 3) >> 2) * (N >> 2) > NT;
+    if (w_shared) {
+      if (big) gemm_nn_impl<8, true>(A, (int)lda, B, (int)ldb, C, (int)ldc, M, N, K, acc);
+      else gemm_nn_impl<4, true>(A, (int)lda, B, (int)ldb, C, (int)ldc, M, N, K, acc);
+    } else {
+      if (big) gemm_nn_impl<8, false>(A, (int)lda, B, (int)ldb, C, (int)ldc, M, N, K, acc);
+      else gemm_nn_impl<4, false>(A, (int)lda, B, (int)ldb, C, (int)ldc, M, N, K, acc);
     }
+    stamp(3);
+  }
+  __device__ __forceinline__ void wcolsum_acc(const float* Mat, int64_t ldm, int N, const float* Wt, int64_t M, float* out, float*, int64_t,
+                                              int64_t ldo = 0) {
+    wcolsum_impl(Mat, (int)ldm, N, Wt, (int)M, out, g_shared, (int)ldo, scratch);
+    stamp(4);
+  }
+  // (+ outE[e * ldoE + n] += sum_m A[m, n] E[m, e]: grad[U | b] = Abar^T E)
+  __device__ __forceinline__ void gemm_tn_acc(const float* A, int64_t lda, const float* S, int64_t lds, float* out, int N, int Kd, int64_t M,
+                                              const float* E, float* outE, int64_t ldoE, float*, int64_t) {
+    gemm_tn_impl(A, (int)lda, S, (int)lds, out, g_shared, N, Kd, (int)M, scratch);
+    stamp(5);
+    if (E) { wcolsum_impl(A, (int)lda, N, E, (int)M, outE, g_shared, (int)ldoE, scratch); stamp(6); }
+  }
+  __device__ __forceinline__ void rowdot(const float* S, int64_t lds, const float* W, const float* b, float* U, int64_t M, int Hp, int o, int C) {
+    rowdot_impl(S, (int)lds, W, b, U, (int)M, Hp, o, C);
+    stamp(7);
+  }
+  __device__ __forceinline__ void zero(void* p, size_t bytes) {
+    float* f = reinterpret_cast<float*>(p);
+    for (int i = threadIdx.x; i < (int)(bytes >> 2); i += NT) f[i] = 0.f;
     __syncthreads();
   }
-
-  // out[(i / cols) ...] column sums with up to four weights per row:
-  //   out[(ldo > 0 ? e * ldo : e * N) + n] += sum_r Wt[r][e] * Mat[r * ldm + n]   (e < 4; Wt == nullptr: plain sum, e = 0)
-  // thread = (column n, row group g of G = NT / N); groups are combined through the scratch in group order.
-  __device__ void wcolsum_acc(const float* __restrict__ Mat, int64_t ldm_, int N, const float* __restrict__ Wt, int64_t M_, float* out,
-                              float*, int64_t, int64_t ldo = 0) {
-    const int ldm = (int)ldm_, M = (int)M_;
-    const int NE = Wt ? 4 : 1;
-    int G = NT / N;
-    if (G * NE * N > SCRATCH_FLOATS) G = SCRATCH_FLOATS / (NE * N);
-    if (G > M) G = M > 0 ? M : 1;
-    const int tid = threadIdx.x, n = tid % N, g = tid / N;
-    if (g < G) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      for (int r = g; r < M; r += G) {
-        const float v = Mat[r * ldm + n];
-        if (Wt) {
-          const float4 w = *reinterpret_cast<const float4*>(Wt + r * 4);
-          a0 = fmaf(w.x, v, a0); a1 = fmaf(w.y, v, a1); a2 = fmaf(w.z, v, a2); a3 = fmaf(w.w, v, a3);
-        } else {
-          a0 += v;
-        }
-      }
-      float* s = scratch + (g * NE) * N + n;
-      s[0] = a0;
-      if (Wt) { s[N] = a1; s[2 * N] = a2; s[3 * N] = a3; }
-    }
-    __syncthreads();
-    for (int i = tid; i < NE * N; i += NT) {
-      float t = 0.f;
-      for (int q = 0; q < G; ++q) t += scratch[q * NE * N + i];
-      const int e = i / N, c = i - e * N;
-      out[(ldo > 0 ? (int64_t)e * ldo : (int64_t)e * N) + c] += t;
-    }
-    __syncthreads();
-  }
-
-  // out[N, Kd] += A^T S over the tile's M rows (+ outE[e * ldoE + n] += sum_m A[m, n] E[m, e]).  4 x 4 register tiles
-  // over (n, kd); when there are fewer tiles than threads the rows are split over thread groups that are combined
-  // through the scratch in group order.
-  __device__ void gemm_tn_acc(const float* __restrict__ A, int64_t lda_, const float* __restrict__ S, int64_t lds_, float* out, int N, int Kd,
-                              int64_t M_, const float* __restrict__ E, float* outE, int64_t ldoE, float*, int64_t) {
-    const int lda = (int)lda_, lds = (int)lds_, M = (int)M_;
-    const int nkg = Kd >> 2, ntiles = (N >> 2) * nkg;
-    int G = NT / ntiles;
-    if (G < 1) G = 1;
-    while (G > 1 && (G - 1) * N * Kd > SCRATCH_FLOATS) --G;
-    for (int t0 = 0; t0 < ntiles * G; t0 += NT) {
-      const int t = t0 + threadIdx.x;
-      const int g = t / ntiles, tt = t - g * ntiles;
-      const bool live = t < ntiles * G;
-      const int ng = tt / nkg, kg = tt - ng * nkg;
-      const int n0 = ng * 4, k0 = kg * 4;
-      float2 c2[4][2];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { c2[i][0] = make_float2(0.f, 0.f); c2[i][1] = make_float2(0.f, 0.f); }
-      if (live) {
-        for (int m = g; m < M; m += G) {
-          const float4 a = *reinterpret_cast<const float4*>(A + m * lda + n0);
-          const float4 s = *reinterpret_cast<const float4*>(S + m * lds + k0);
-          const float2 slo = make_float2(s.x, s.y), shi = make_float2(s.z, s.w);
-          float2 a2;
-          a2 = make_float2(a.x, a.x); c2[0][0] = __ffma2_rn(a2, slo, c2[0][0]); c2[0][1] = __ffma2_rn(a2, shi, c2[0][1]);
-          a2 = make_float2(a.y, a.y); c2[1][0] = __ffma2_rn(a2, slo, c2[1][0]); c2[1][1] = __ffma2_rn(a2, shi, c2[1][1]);
-          a2 = make_float2(a.z, a.z); c2[2][0] = __ffma2_rn(a2, slo, c2[2][0]); c2[2][1] = __ffma2_rn(a2, shi, c2[2][1]);
-          a2 = make_float2(a.w, a.w); c2[3][0] = __ffma2_rn(a2, slo, c2[3][0]); c2[3][1] = __ffma2_rn(a2, shi, c2[3][1]);
-        }
-        if (g > 0) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<float4*>(scratch + (g - 1) * N * Kd + (n0 + i) * Kd + k0) = make_float4(c2[i][0].x, c2[i][0].y, c2[i][1].x, c2[i][1].y);
-        }
-      }
-      if (G > 1) __syncthreads();
-      if (live && g == 0) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float4 v = make_float4(c2[i][0].x, c2[i][0].y, c2[i][1].x, c2[i][1].y);
-          for (int q = 1; q < G; ++q) {
-            const float4 o = *reinterpret_cast<const float4*>(scratch + (q - 1) * N * Kd + (n0 + i) * Kd + k0);
-            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-          }
-          float4* p = reinterpret_cast<float4*>(out + (n0 + i) * Kd + k0);
-          const float4 o = *p;
-          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-          *p = v;
-        }
-      }
-      if (G > 1) __syncthreads();   // (G > 1 implies a single pass of the t0 loop)
-    }
-    __syncthreads();
-    if (E) wcolsum_acc(A, lda_, N, E, M_, outE, nullptr, 0, ldoE);
-  }
-
-  // u[r][m] = S[r, :] . W[m, :] (+ b[m] on value rows); one thread per row, the column index rotated by the lane so
-  // that a warp's 32 rows hit 32 different banks
-  __device__ void rowdot(const float* __restrict__ S, int64_t lds_, const float* __restrict__ W, const float* __restrict__ b, float* U, int64_t M_, int Hp,
-                         int o, int C) {
-    const int lds = (int)lds_, M = (int)M_;
-    for (int r = threadIdx.x; r < M; r += NT) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      const float* s = S + r * lds;
-      int j = threadIdx.x & 31;   // Hp is a multiple of 32
-      for (int q = 0; q < Hp; ++q) {
-        const float sv = s[j];
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-          if (m < o) acc[m] = fmaf(sv, W[m * Hp + j], acc[m]);
-        j = (j + 1 == Hp) ? 0 : j + 1;
-      }
-      const bool vrow = (r % C) == 0;
-      float4 out;
-      out.x = acc[0] + (vrow ? b[0] : 0.f);
-      out.y = (1 < o) ? acc[1] + (vrow ? b[1] : 0.f) : 0.f;
-      out.z = (2 < o) ? acc[2] + (vrow ? b[2] : 0.f) : 0.f;
-      out.w = (3 < o) ? acc[3] + (vrow ? b[3] : 0.f) : 0.f;
-      *reinterpret_cast<float4*>(U + r * 4) = out;
-    }
-    __syncthreads();
-  }
-  __device__ void zero(void*, size_t) {}
   __device__ void copy(void*, const void*, size_t) {}
-};
-
-enum { PROB_HEAT = 0, PROB_ODE = 1 };   // ODE covers simple_ode and FitzHugh-Nagumo (OdeArgs::fhn)
-
-struct TileParams {
-  NetDims n; PackedLayout pl;
-  const float* Wp;        // packed weights (plain copy), global memory
-  float* slots;           // [nslots][g_total] zero-initialised partial gradient accumulators
-  int64_t B;              // points of this launch
-  int32_t P;              // points per tile
-  int32_t nslots_per_cta;
-  int32_t w_smem, g_smem; // stage the weights / keep the accumulators in shared memory
-  uint32_t w_floats, g_floats, lp_floats, tile_bytes;
-  HeatArgs heat;
-  OdeArgs ode;
 };
 
 // shared memory: [scratch][weights if w_smem][accumulators if g_smem][Lp][tile region]
@@ -265,6 +353,9 @@ __global__ void __launch_bounds__(NT, 1) tile_step_kernel(const __grid_constant_
   BK bk;
   bk.scratch = sp; sp += SCRATCH_FLOATS;
   bk.hl_stride = 0;
+  bk.w_shared = prm.w_smem != 0; bk.g_shared = prm.g_smem != 0;
+  bk.prof = blockIdx.x == 0 ? prm.prof : nullptr; bk.prof_i = 0; bk.prof_n = prm.prof_n;
+  bk.stamp(0);
   TileCtx c(prm.n, prm.pl);
   const int tid = threadIdx.x;
   if (prm.w_smem) {
@@ -287,6 +378,8 @@ __global__ void __launch_bounds__(NT, 1) tile_step_kernel(const __grid_constant_
     c.Gp = slot0;
   }
   c.Lp = sp; sp += prm.lp_floats;
+  bk.coords = sp; bk.coords_cap = (int)prm.coord_floats; sp += prm.coord_floats;
+  float* Ip = sp; sp += prm.ip_floats;   // Fredholm: running integral / residual gradient per point of the block
   char* region = reinterpret_cast<char*>(sp);
   __syncthreads();
 
@@ -298,7 +391,8 @@ __global__ void __launch_bounds__(NT, 1) tile_step_kernel(const __grid_constant_
     const int64_t r = (prm.B - p0 < prm.P) ? prm.B - p0 : prm.P;
     Carver cv(region, prm.tile_bytes);
     if (PROB == PROB_HEAT) heat_chunk(pipe, cv, 0, prm.heat, p0, r);
-    else ode_like_chunk(pipe, cv, 0, prm.ode, p0, r);
+    else if (PROB == PROB_ODE) ode_like_chunk(pipe, cv, 0, prm.ode, p0, r);
+    else fredholm_block(pipe, cv, 0, prm.fred, p0, r, prm.J, Ip);
     if (++in_seg == FLUSH_TILES && slot + 1 < prm.nslots_per_cta) {   // start a new FP32 accumulation segment
       if (prm.g_smem) {
         float* dst = slot0 + (size_t)slot * prm.g_floats;

@@ -1,0 +1,34 @@
+// Launch parameters and shared-memory budget of the resident-tile step kernels (dgmk_tile.cuh): the part the host
+// side (CudaBackend::tile_step in dgmk_cuda.cu) and the kernels' translation unit (dgmk_tile.cu) share.
+#pragma once
+#include <stdint.h>
+#include "dgmk_steps.h"
+
+namespace dgmk {
+namespace tk {
+
+constexpr int NT = 512;                 // threads per CTA (one CTA per SM)
+constexpr int SCRATCH_FLOATS = 4096;    // cross-group reduction scratch (16 KB)
+constexpr int SMEM_MAX = 232448;        // 227 KB opt-in limit per CTA on sm_100
+constexpr int FLUSH_TILES = 256;        // tiles per FP32 accumulation segment
+
+enum { PROB_HEAT = 0, PROB_ODE = 1, PROB_FRED = 2 };   // ODE covers simple_ode and FitzHugh-Nagumo (OdeArgs::fhn)
+
+struct TileParams {
+  NetDims n; PackedLayout pl;
+  const float* Wp;        // packed weights (plain copy), global memory
+  float* slots;           // [nslots][g_total] zero-initialised partial gradient accumulators
+  int64_t B;              // points of this launch
+  int32_t P;              // points per tile
+  int32_t nslots_per_cta;
+  int32_t w_smem, g_smem; // stage the weights / keep the accumulators in shared memory
+  uint32_t w_floats, g_floats, lp_floats, coord_floats, ip_floats, tile_bytes;
+  int32_t J;              // Fredholm: quadrature nodes per sub-tile (rows per sub-tile = P * J)
+  HeatArgs heat;
+  OdeArgs ode;
+  FredArgs fred;
+  long long* prof; int32_t prof_n;   // stage timeline of CTA 0 (diagnostic; nullptr = off)
+};
+
+}  // namespace tk
+}  // namespace dgmk

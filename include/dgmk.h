@@ -144,6 +144,8 @@ void dgmk_set_gemm_engine(int engine);
  * per-CTA gradient accumulation) in ONE persistent kernel with the activation stash and the packed weights in
  * shared memory (csrc/dgmk_tile.cuh); 0: the layer-wise path for every hidden size */
 void dgmk_set_tile_engine(int on);
+/* stage timeline of CTA 0 of the resident-tile kernel: (clock64, stage kind) pairs into buf (device, 2 * n int64) */
+void dgmk_tile_profile(long long* buf, int n);
 /* Per-kernel-class timing with CUDA events on the launch stream.  dgmk_profile(1) clears and
  * starts, dgmk_profile(0) stops; dgmk_profile_read synchronises the recorded events and returns the
  * class's summed duration [ms], launches, ALGORITHMIC flops and bytes.  Classes: 0 weight gradient,

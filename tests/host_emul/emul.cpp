@@ -10,7 +10,12 @@
 #include "../../differential_equations_dnn_b200/csrc/dgmk_capi_impl.h"
 
 namespace {
+int g_fred_nodes = 0, g_fred_points = 0;   // dgmk_emul_set_fredholm_blocks: the sub-tiled Fredholm body (dgmk_steps.h)
+bool g_inplace_rev = false;   // dgmk_emul_set_inplace: run the reverse pass in the resident-tile step's in-place mode
 struct HostBackend : dgmk::BackendTraitsAll {
+  bool inplace_rev() const { return g_inplace_rev; }
+  int fredholm_block_nodes() const { return g_fred_nodes; }
+  int fredholm_block_points() const { return g_fred_points; }
   bool bad_bt = false;
   int64_t hl_stride = 0;
   explicit HostBackend(void*) {}
@@ -84,6 +89,8 @@ struct HostBackend : dgmk::BackendTraitsAll {
 }  // namespace
 
 DGMK_DEFINE_C_API(HostBackend, "host-emulation (tests only)")
+extern "C" void dgmk_emul_set_inplace(int on) { g_inplace_rev = on != 0; }
+extern "C" void dgmk_emul_set_fredholm_blocks(int points, int nodes) { g_fred_points = points; g_fred_nodes = nodes; }
 
 // ---- unit checks of functor code that only the CUDA backend's fused path calls (same templates, host
 // instantiation): the structural input-map adjoint and the V-units-per-thread DgmRev1 stage ------------------

@@ -114,6 +114,40 @@ def test_step_matches_reference(lib, prob, name):
     check(lib, g, loss, grad)
 
 
+@pytest.mark.parametrize("prob,name", [c for c in CASES if c[0] != "fredholm"])
+def test_inplace_reverse_matches_reference(lib, prob, name):
+    """The reverse pass of the resident-tile step (csrc/dgmk_tile.cuh) overwrites the forward stash as it consumes
+    it (pre-activation cotangents over the a-form gates, (s*R)bar over s*R, one state-cotangent buffer): the same
+    orchestration template in that mode, host loops as the backend, against the executed reference -- and
+    bit-identical to the out-of-place mode."""
+    g = golden(name)
+    loss0, grad0 = run_step(lib, prob, g)
+    lib.dgmk_emul_set_inplace(1)
+    try:
+        loss, grad = run_step(lib, prob, g)
+    finally:
+        lib.dgmk_emul_set_inplace(0)
+    check(lib, g, loss, grad)
+    assert loss == loss0 and np.array_equal(grad, grad0)
+
+
+@pytest.mark.parametrize("name", golden_names("fredholm_"))
+@pytest.mark.parametrize("points,nodes,inplace", [(8, 3, 1), (5, 64, 1), (1, 1, 0), (32, 2, 0)])
+def test_fredholm_blocks_match_reference(lib, name, points, nodes, inplace):
+    """The Fredholm body the resident-tile kernel runs (dgmk_steps.h fredholm_block: blocks of points, their k nodes
+    walked in sub-tiles, node rows evaluated twice when they span several sub-tiles) with host loops as the backend:
+    ragged blocks, sub-tiles that do and do not divide k, one sub-tile holding all k nodes."""
+    g = golden(name)
+    lib.dgmk_emul_set_fredholm_blocks(points, nodes)
+    lib.dgmk_emul_set_inplace(inplace)
+    try:
+        loss, grad = run_step(lib, "fredholm", g)
+    finally:
+        lib.dgmk_emul_set_fredholm_blocks(0, 0)
+        lib.dgmk_emul_set_inplace(0)
+    check(lib, g, loss, grad)
+
+
 @pytest.mark.parametrize("prob,name", [("heat", "heat_dgm_h32l1"), ("fredholm", "fredholm_dgmraw_h32l1_k7"),
                                        ("fhn", "fhn_dgm_h64l2")])
 def test_chunked_equals_unchunked(lib, prob, name):

@@ -12,7 +12,7 @@ from differential_equations_dnn_b200 import _cabi, kernels as K  # noqa: E402
 from test_gpu_kernels import run, desc_of  # noqa: E402
 
 lib = _cabi.load()
-names = sys.argv[1:] or [n for p in ("heat_", "ode_", "fhn_") for n in golden_names(p) if "driver" not in n]
+names = sys.argv[1:] or [n for p in ("heat_", "ode_", "fhn_", "fredholm_") for n in golden_names(p) if "driver" not in n]
 for name in names:
     prob = name.split("_")[0]
     g = golden(name)
