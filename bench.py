@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--k", type=int, default=1024, help="fredholm: quadrature nodes per point")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-eager", action="store_true")
+    ap.add_argument("--no-driver-latency", action="store_true")
     return ap.parse_args()
 
 
@@ -525,6 +526,7 @@ def main():
         except Exception as e:
             cuda_eager = {"error": repr(e)}
 
+    drv = driver_latency(pk, wl, dev) if (world == 1 and not a.no_driver_latency) else None
     h2d = sum(t.numel() * 4 for t in host)
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": max(world, 1), "steps": a.steps, "warmup": W,
@@ -533,11 +535,49 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": e_step},
         "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "cuda_eager_baseline": cuda_eager,
+        "driver_latency": drv,
         "node_evals_per_sec": value * (wl.k + 1) if wl.name == "fredholm" else None,
         "loss_last": float(last.detach()) if hasattr(last, "detach") else float(last), "wall_ms_per_step": wall_ms / a.steps}), flush=True)
     if dist.is_initialized():
         dist.barrier()
         dist.destroy_process_group()
+
+
+def driver_latency(pk, wl, dev):
+    """The reference's own regime: its training driver at the SHIPPED batch size (heat.py / simple_ode.py:
+    64 rows, fitzhugh_nagumo.py: 100, fredholm.py: 32 rows x k = 50) is launch-bound.  us per iteration of this package's
+    `minimize_loss_dgm` for the workload's network -- sampler, fused step, Adam, loss record -- launched from Python
+    (eager) and replayed from a CUDA graph (cuda_graph=True; capture cost excluded by differencing two run lengths)."""
+    import contextlib
+    import io
+    rows = {"heat": 64, "ode": 64, "fhn": 100, "fredholm": 32}[wl.name]
+
+    def run(n, graph):
+        net = wl.build_net(pk).to(dev)
+        with contextlib.redirect_stdout(io.StringIO()):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if wl.name == "heat":
+                pk.heat.minimize_loss_dgm(net, iterations=n, batch_size=rows, lrate=1e-4, cuda_graph=graph)
+            elif wl.name == "ode":
+                pk.simple_ode.minimize_loss_dgm(net, y_ic=2.0, iterations=n, batch_size=rows, lrate=1e-4, cuda_graph=graph)
+            elif wl.name == "fhn":
+                pk.fitzhugh_nagumo.minimize_loss_dgm(net, torch.zeros([rows, 2], device=dev), iterations=n, batch_size=rows,
+                                                     lrate=1e-4, sampler="grid", cuda_graph=graph)
+            else:
+                pk.fredholm.minimize_loss_dgm(net, iterations=n, batch_size=rows, lrate=1e-4, k=50, cuda_graph=graph)
+            torch.cuda.synchronize()
+        return time.perf_counter() - t0
+    try:
+        run(30, False), run(30, True)   # warm the caches both modes rely on
+        eager = (run(330, False) - run(30, False)) / 300
+        graph = (run(1230, True) - run(230, True)) / 1000
+        return {"rows": rows, "k": 50 if wl.name == "fredholm" else None, "eager_us_per_iteration": eager * 1e6,
+                "cuda_graph_us_per_iteration": graph * 1e6,
+                "what": "this package's minimize_loss_dgm at the reference driver's shipped batch size (sampler + fused step + "
+                        "fused Adam + loss record per iteration); differences of two run lengths, capture excluded"}
+    except Exception as e:
+        return {"error": repr(e)}
 
 
 def roofline(lib, wl, prof, B, ms_step, dev):

@@ -38,7 +38,7 @@ def dgm_loss_func(net, x, x0, xbd1, xbd2, x_bd1, x_bd2):
     return ag.HeatStepFn.apply(net, x, x0, xbd1, xbd2, x_bd1, x_bd2, 1.0, *ag.params_of(net))
 
 
-def _minimize_graphed(net, iterations, batch_size, lrate, warmup=11):
+def _minimize_graphed(net, iterations, batch_size, lrate, warmup=11, xbd2_value=torch.pi):
     """The training loop with one captured iteration replayed (`_loop.graphed_loop`): same RNG stream,
     same arithmetic as the eager loop."""
     device = _device()
@@ -47,7 +47,7 @@ def _minimize_graphed(net, iterations, batch_size, lrate, warmup=11):
     optimizer = FusedAdam(net.parameters(), lr=lrate, capturable=True)
     t0 = torch.zeros([batch_size, 1], device=device)
     xbd1 = torch.zeros([batch_size, 1], device=device)
-    xbd2x = torch.ones([batch_size, 1], device=device) * torch.pi
+    xbd2x = torch.ones([batch_size, 1], device=device) * xbd2_value
     xbd2y = torch.zeros([batch_size, 1], device=device)
 
     def step():
@@ -69,7 +69,7 @@ def _minimize_graphed(net, iterations, batch_size, lrate, warmup=11):
 
 
 @fn_timer
-def minimize_loss_dgm(net, iterations=1000, batch_size=32, lrate=1e-4, cuda_graph=False):
+def minimize_loss_dgm(net, iterations=1000, batch_size=32, lrate=1e-4, cuda_graph=False, xbd2_value=torch.pi):
     """The reference's training driver (heat.py:98-149): same sampler, same Adam
     defaults, returns (net, train_loss: list[float]).  Differences that do not change
     results: losses stay on the device and are read back once at the end (plus every
@@ -79,14 +79,14 @@ def minimize_loss_dgm(net, iterations=1000, batch_size=32, lrate=1e-4, cuda_grap
     inside `dgm_loss_func`.  `cuda_graph=True` (single GPU) replays one captured
     iteration instead of launching it from Python (`_minimize_graphed`)."""
     if cuda_graph and not parallel.is_enabled():
-        return _minimize_graphed(net, iterations, batch_size, lrate)
+        return _minimize_graphed(net, iterations, batch_size, lrate, xbd2_value=xbd2_value)
     device = _device()
     parallel.sync_parameters(net)            # data parallel: rank 0's weights everywhere
     gen = parallel.sampler_generator(device)  # ... and per-rank rows (None on one GPU: the default RNG stream)
     optimizer = FusedAdam(net.parameters(), lr=lrate)
     t0 = torch.zeros([batch_size, 1], device=device)
     xbd1 = torch.zeros([batch_size, 1], device=device)
-    xbd2x = torch.ones([batch_size, 1], device=device) * torch.pi
+    xbd2x = torch.ones([batch_size, 1], device=device) * xbd2_value
     xbd2y = torch.zeros([batch_size, 1], device=device)
     losses = []
     for i in range(iterations):

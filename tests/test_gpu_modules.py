@@ -263,7 +263,6 @@ def test_simple_ode_end_to_end():
     assert len(losses) == 5000 and losses[-1] < losses[0]
     sol = simple_ode.gridEvaluation(net, nodes=25)
     mae = np.abs(sol - simple_ode.exact_solution(np.linspace(0, 1.0, 25))).mean()
-    assert abs(mae - 0.00253) < 1e-3 + 0.00253, mae   # same ballpark as the reference, never worse by 1e-3
     assert mae < 0.00253 + 1e-3, mae
 
 
@@ -279,6 +278,85 @@ def test_heat_end_to_end_dgm():
     mae, rmse = np.abs(err).mean(), np.sqrt((err ** 2).mean())
     print("heat e2e: final loss", losses[-1], "MAE", mae, "RMSE", rmse)
     assert mae < 2.0e-4 + 1e-3 and rmse < 2.5e-4 + 1e-3
+
+
+def _heat_grid_error(net):
+    from differential_equations_dnn_b200 import heat
+    err = heat.gridEvaluation(net, nodes=40) - heat.exact_solution(nodes=40)   # heat.py:152-172, :36-47
+    return float(np.abs(err).mean()), float(np.sqrt((err ** 2).mean()))
+
+
+def test_heat_end_to_end_headline_net_three_seeds():
+    """north_star: final-solution L2 error within 1e-3 of the reference after the same iteration count.  The headline
+    network, heat + dgm_net.DGM(2,1,128,3), at the reference driver's 15000 its x 64 rows, lr 1e-4 (heat.py:178-190),
+    seeds 0 / 1 / 2 (SURVEY 8c asks for >= 3 seeds there: the reference lands at RMSE 1.62e-3, MAE 1.33e-3 with seed 0,
+    BASELINE.md); the CUDA-graph driver makes a run ~12 s.  Criterion on the MEAN over the seeds, and no seed diverges."""
+    from differential_equations_dnn_b200 import dgm_net, heat
+    maes, rmses = [], []
+    for seed in (0, 1, 2):
+        torch.manual_seed(seed)
+        net = dgm_net.DGM(input_dim=2, output_dim=1, hidden_size=128, num_layers=3).cuda()
+        net, losses = heat.minimize_loss_dgm(net, iterations=15000, batch_size=64, lrate=1e-4, cuda_graph=True)
+        assert len(losses) == 15000 and np.all(np.isfinite(losses)) and np.mean(losses[-100:]) < 1e-3
+        mae, rmse = _heat_grid_error(net)
+        print(f"heat DGM(2,1,128,3) seed {seed}: final loss {losses[-1]:.2e} MAE {mae:.2e} RMSE {rmse:.2e}")
+        maes.append(mae); rmses.append(rmse)
+    assert np.mean(rmses) < 1.62e-3 + 1e-3 and np.mean(maes) < 1.33e-3 + 1e-3, (maes, rmses)
+    assert max(rmses) < 1e-2, rmses
+
+
+def test_heat_end_to_end_tanh_mlp():
+    """heat + MLP(2,1,128,3, tanh) (the paper's network), 15000 its x 64: reference MAE 3.1e-4 / RMSE 3.8e-4."""
+    from differential_equations_dnn_b200 import neural_networks as nn_, heat
+    torch.manual_seed(0)
+    net = nn_.MLP(input_dim=2, output_dim=1, hidden_size=128, num_layers=3, activation="tanh").cuda()
+    net, losses = heat.minimize_loss_dgm(net, iterations=15000, batch_size=64, lrate=1e-4, cuda_graph=True)
+    mae, rmse = _heat_grid_error(net)
+    print(f"heat MLP tanh: final loss {losses[-1]:.2e} MAE {mae:.2e} RMSE {rmse:.2e}")
+    assert mae < 3.1e-4 + 1e-3 and rmse < 3.8e-4 + 1e-3, (mae, rmse)
+
+
+def test_fredholm_end_to_end():
+    """fredholm.py as shipped: neural_networks.DGM(1,1,32), 3000 its x 32 rows, k = 50, lr 1e-4 (fredholm.py:143-181);
+    MAE vs 2 sin x on 50 nodes of [0, pi/2].  Reference (seed 0, CPU RNG stream): MAE 0.00932, RMSE 0.01082.  The loss
+    is a Monte-Carlo estimate and the GPU sampler draws a different stream, so three seeds are run and the criterion
+    (within 1e-3 of the reference) is applied to their mean."""
+    from differential_equations_dnn_b200 import neural_networks as nn_, fredholm
+    maes, rmses = [], []
+    for seed in (0, 1, 2):
+        torch.manual_seed(seed)
+        net = nn_.DGM(input_dim=1, output_dim=1, hidden_size=32).cuda()
+        net, losses = fredholm.minimize_loss_dgm(net, iterations=3000, batch_size=32, lrate=1e-4, k=50, cuda_graph=True)
+        assert len(losses) == 3000 and np.all(np.isfinite(losses))
+        sol = fredholm.gridEvaluation(net, nodes=50)
+        err = sol - fredholm.exact_solution(np.linspace(0, np.pi / 2.0, 50))
+        maes.append(float(np.abs(err).mean())); rmses.append(float(np.sqrt((err ** 2).mean())))
+        print(f"fredholm seed {seed}: final loss {losses[-1]:.2e} MAE {maes[-1]:.2e} RMSE {rmses[-1]:.2e}")
+    assert np.mean(maes) < 0.00932 + 1e-3 and np.mean(rmses) < 0.01082 + 1e-3, (maes, rmses)
+
+
+def test_trial_launcher_matches_serial_objective():
+    """N3: `parallel.run_trials` with the port of objectiveRay (optimize_heat_ray.py:133-157) returns, on one GPU, the
+    losses of calling the objective serially; the batch-size study (batchsize_effect_heat.py:186-202) runs its trials
+    through the same launcher, quirks of the shipped loop included (every curve trains with batch 64)."""
+    from differential_equations_dnn_b200 import optimize_heat_ray as ohr, batchsize_effect_heat as bse, parallel
+    configs = [dict(c, n_iters=150) for c in parallel.sample_search_space(3, 0)]
+    assert all(1 <= c["batch_size"] < 512 and 1e-4 <= c["lrate"] <= 1e-1 for c in configs)
+
+    def obj(cfg):
+        torch.manual_seed(5)
+        torch.cuda.manual_seed(5)
+        return ohr.objectiveRay(cfg)
+    res = parallel.run_trials(obj, configs)
+    serial = [obj(c) for c in configs]
+    assert [r["loss"] for r in res] == serial and all(np.isfinite(serial))
+    assert parallel.best_trial(res)["loss"] == min(serial)
+    torch.manual_seed(6)
+    study = bse.run_study(n_iters=120, n_runs=2, n_batches=2)
+    assert [r["config"]["batch_size"] for r in study] == [1, 2, 4] and all(np.isfinite(r["loss"]) for r in study)
+    torch.manual_seed(6)
+    fixed = bse.run_study(n_iters=120, n_runs=2, n_batches=2, fix_batch_size=True, fresh_net=True)
+    assert len(fixed) == 3 and all(np.isfinite(r["loss"]) for r in fixed)
 
 
 def test_cuda_graph_driver_matches_eager():
