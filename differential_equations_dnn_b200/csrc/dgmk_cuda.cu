@@ -647,7 +647,7 @@ struct CudaBackend : BackendTraitsAll {
     // path, which streams large GEMMs through HBM, is faster; at hidden size 32 the tile step wins or ties at
     // every batch size.  g_tile == 2 forces the tile step.
     const int64_t tile_rows = P * (cls == DGMK_WS_HEAT ? 4 : 2);
-    if (g_tile == 1 && c.n.Hp > 32 && B > 4096 && !(tile_rows >= 48 && B <= 32768)) return false;
+    if (g_tile == 1 && c.n.Hp > 32 && B > 4096 && !(tile_rows >= 48 && B <= 16384)) return false;
     // spread the points evenly over the tiles (same tile count, smaller ragged tail)
     const int64_t nt0 = (B + P - 1) / P;
     P = (B + nt0 - 1) / nt0;

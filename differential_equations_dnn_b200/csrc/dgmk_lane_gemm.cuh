@@ -85,7 +85,7 @@ constexpr int EPI_WARPS = 16;                        // 4 per scheduler: the fus
 constexpr int EPI_ROWS = NR / (EPI_WARPS / 4);       // accumulator columns (= rows) per epilogue thread
 constexpr int EPI_GROUPS = EPI_ROWS / 8;
 constexpr int NT = (W_EPI + EPI_WARPS) * 32;
-constexpr int REGS_PRODUCER = 40, REGS_EPI = 96;     // must fit the launch allocation (768 x 80): 256 x 40 + 512 x 96 = 59392
+constexpr int REGS_PRODUCER = 32, REGS_EPI = 104;    // must fit the launch allocation (768 x 80 = 61440): 256 x 32 + 512 x 104 = 61440
 constexpr int NCONS = EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int TM_WHI = 0, TM_WLO = KTOT, TM_ACC = 2 * KTOT;   // TMEM column map

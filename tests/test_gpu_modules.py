@@ -318,9 +318,11 @@ def test_heat_end_to_end_tanh_mlp():
 
 def test_fredholm_end_to_end():
     """fredholm.py as shipped: neural_networks.DGM(1,1,32), 3000 its x 32 rows, k = 50, lr 1e-4 (fredholm.py:143-181);
-    MAE vs 2 sin x on 50 nodes of [0, pi/2].  Reference (seed 0, CPU RNG stream): MAE 0.00932, RMSE 0.01082.  The loss
-    is a Monte-Carlo estimate and the GPU sampler draws a different stream, so three seeds are run and the criterion
-    (within 1e-3 of the reference) is applied to their mean."""
+    MAE vs 2 sin x on 50 nodes of [0, pi/2].  The loss is a Monte-Carlo estimate (k = 50 nodes per point) and the result
+    depends on the seed: the UNMODIFIED reference driver (oracle/_ref, CPU, torch.manual_seed(s)) gives, for s = 0..3,
+    MAE 0.00932 / 0.01040 / 0.01316 / 0.00626 and RMSE 0.01082 / 0.01162 / 0.01543 / 0.00787 (means 0.00979 / 0.01144;
+    seed 0 is the BASELINE.md row).  The GPU sampler draws a different stream, so three seeds are run here and the
+    criterion -- within 1e-3 of the reference -- is applied mean against mean."""
     from differential_equations_dnn_b200 import neural_networks as nn_, fredholm
     maes, rmses = [], []
     for seed in (0, 1, 2):
@@ -332,7 +334,8 @@ def test_fredholm_end_to_end():
         err = sol - fredholm.exact_solution(np.linspace(0, np.pi / 2.0, 50))
         maes.append(float(np.abs(err).mean())); rmses.append(float(np.sqrt((err ** 2).mean())))
         print(f"fredholm seed {seed}: final loss {losses[-1]:.2e} MAE {maes[-1]:.2e} RMSE {rmses[-1]:.2e}")
-    assert np.mean(maes) < 0.00932 + 1e-3 and np.mean(rmses) < 0.01082 + 1e-3, (maes, rmses)
+    assert np.mean(maes) < 0.00979 + 1e-3 and np.mean(rmses) < 0.01144 + 1e-3, (maes, rmses)
+    assert max(rmses) < 0.01543 + 1e-3, rmses   # no seed worse than the reference's worst
 
 
 def test_trial_launcher_matches_serial_objective():
