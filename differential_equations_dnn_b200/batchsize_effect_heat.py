@@ -37,7 +37,7 @@ def loss_curve(net, batch_size, n_iters, n_runs, fix_batch_size=False, fresh_net
     return running.mean(axis=0)
 
 
-def run_study(n_iters=15000, n_runs=5, n_batches=10, fix_batch_size=False, fresh_net=False, cuda_graph=True):
+def run_study(n_iters=15000, n_runs=5, n_batches=10, fix_batch_size=False, fresh_net=False, cuda_graph=True, trial_seed=1234):
     """-> [{"trial", "config": {"batch_size"}, "loss" (last point of the mean curve), "curve"}] for 2^0 .. 2^n_batches."""
     with contextlib.redirect_stdout(io.StringIO()):
         shared = None if fresh_net else MLP(input_dim=2, output_dim=1, hidden_size=128, num_layers=3).cuda()
@@ -49,7 +49,7 @@ def run_study(n_iters=15000, n_runs=5, n_batches=10, fix_batch_size=False, fresh
         curves[cfg["batch_size"]] = c
         return c[-1]
     configs = [{"batch_size": 2 ** i} for i in range(n_batches + 1)]
-    results = parallel.run_trials(objective, configs)
+    results = parallel.run_trials(objective, configs, seed=trial_seed)
     for r in results:   # curves of the trials this rank ran (rank 0 holds all of them on one GPU)
         c = curves.get(r["config"]["batch_size"])
         if c is not None:

@@ -43,11 +43,11 @@ def objectiveRay(config, cuda_graph=True, quiet=True):
     return loss_dgm[-1]
 
 
-def optimizeHeat(num_samples=10, seed=0, objective=None):
+def optimizeHeat(num_samples=10, seed=0, objective=None, trial_seed=1234):
     """optimize_heat_ray.py:160-203: `num_samples` trials, round-robin one per GPU (rank), best config by final loss.
     Returns (best_config, all trial records)."""
     configs = parallel.sample_search_space(num_samples, seed)
-    results = parallel.run_trials(objective or objectiveRay, configs)
+    results = parallel.run_trials(objective or objectiveRay, configs, seed=trial_seed)
     return parallel.best_trial(results)["config"], results
 
 
@@ -59,7 +59,6 @@ def main(argv=None):
     ap.add_argument("--out", default=None)
     a = ap.parse_args(argv)
     parallel.init_from_env()
-    torch.manual_seed(1234)
     t0 = time.perf_counter()
     best, results = optimizeHeat(a.num_samples, a.seed)
     wall = time.perf_counter() - t0

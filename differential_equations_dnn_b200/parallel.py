@@ -135,16 +135,22 @@ def sample_search_space(n, seed=0):
     return out
 
 
-def run_trials(objective, configs):
+def run_trials(objective, configs, seed=None):
     """Round-robin `configs` over the ranks (one GPU each, zero communication while
     training), gather `{config, loss}` records on every rank.  `objective(config)`
-    returns the final loss, like objectiveRay -> session.report (optimize_heat_ray.py:157)."""
+    returns the final loss, like objectiveRay -> session.report (optimize_heat_ray.py:157).
+    `seed`: trial i starts from torch.manual_seed(seed + i), so a trial's result does not depend on how many
+    GPUs the sweep runs on or on which rank it lands (the kernels are deterministic)."""
     if dist.is_initialized():
         R, r = dist.get_world_size(), dist.get_rank()
     else:
         R, r = 1, 0
     mine = [(i, c) for i, c in enumerate(configs) if i % R == r]
-    results = [{"trial": i, "config": c, "loss": float(objective(c)), "rank": r} for i, c in mine]
+    results = []
+    for i, c in mine:
+        if seed is not None:
+            torch.manual_seed(seed + i)
+        results.append({"trial": i, "config": c, "loss": float(objective(c)), "rank": r})
     if R > 1:
         gathered = [None] * R
         dist.all_gather_object(gathered, results)
