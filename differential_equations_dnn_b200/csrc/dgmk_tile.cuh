@@ -33,16 +33,14 @@ struct TileCtx {
   __device__ TileCtx(const NetDims& n_, const PackedLayout& pl_) : n(n_), pl(pl_), Wp(nullptr), Gp(nullptr), part(nullptr), part_n(0), Lp(nullptr) {}
 };
 
-// 16-byte shared-memory accesses by 32-bit address (left to itself ptxas splits a float4 access through a pointer it
-// only ASSUMES to be shared into four scalar LDS)
-__device__ __forceinline__ uint32_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ float4 lds4(uint32_t a) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void sts4(uint32_t a, const float4& v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+// The CTA's dynamic shared memory (every extern __shared__ array of a kernel names the same block).  The stage
+// primitives below receive generic pointers into it; rebasing them on this symbol tells the compiler their address
+// space, so that plain C++ accesses compile to LDS / STS (.128 for float4) with 32-bit addresses and full freedom to
+// schedule -- neither the generic LD / ST of an unknown pointer nor order-pinned inline asm.
+extern __shared__ __align__(16) float g_tile_smem[];
+template <class T>
+__device__ __forceinline__ T* shp(T* p) {
+  return reinterpret_cast<T*>(g_tile_smem + (reinterpret_cast<const float*>(p) - reinterpret_cast<const float*>(g_tile_smem)));
 }
 
 // ---- CTA-cooperative stage primitives (free functions, NOT inlined: one copy per translation unit keeps the
@@ -51,33 +49,33 @@ __device__ __forceinline__ void sts4(uint32_t a, const float4& v) {
 // C[M,N] (+)= A[M,K] B[K,N]; A, C in shared memory, B = packed weights (shared memory: BSH, or L2).  TM x 4 register
 // tiles on packed FFMA2, the tile index walks N fastest (a warp shares its A rows by broadcast).
 template <int TM, bool BSH>
-__device__ __noinline__ void gemm_nn_impl(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C,
+__device__ __noinline__ void gemm_nn_impl(const float* __restrict__ A_, int lda, const float* __restrict__ B_, int ldb, float* __restrict__ C_,
                                           int ldc, int M, int N, int K, bool acc) {
-  const uint32_t As = saddr(A), Cs = saddr(C), Bs = BSH ? saddr(B) : 0u;
+  const float* A = shp(A_);
+  float* C = shp(C_);
+  const float* B = BSH ? shp(B_) : B_;
   const int ncg = N >> 2, ntiles = ((M + TM - 1) / TM) * ncg;
   for (int t = threadIdx.x; t < ntiles; t += NT) {
     const int rg = t / ncg, cg = t - rg * ncg;
     const int r0 = rg * TM, n0 = cg * 4;
-    uint32_t ar[TM];
+    const float* ar[TM];
 #pragma unroll
-    for (int i = 0; i < TM; ++i) ar[i] = As + (uint32_t)((r0 + i < M ? r0 + i : M - 1) * lda) * 4u;   // clamp: rows >= M are computed, not stored
+    for (int i = 0; i < TM; ++i) ar[i] = A + (r0 + i < M ? r0 + i : M - 1) * lda;   // clamp: rows >= M are computed, not stored
     float2 c2[TM][2];
 #pragma unroll
     for (int i = 0; i < TM; ++i) { c2[i][0] = make_float2(0.f, 0.f); c2[i][1] = make_float2(0.f, 0.f); }
-    uint32_t bs = Bs + (uint32_t)n0 * 4u;
     const float* bp = B + n0;
-    const uint32_t bstep = (uint32_t)ldb * 4u;
 #pragma unroll 2
     for (int k0 = 0; k0 < K; k0 += 4) {
       float4 b4[4];
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        if (BSH) { b4[kk] = lds4(bs); bs += bstep; }
+        if (BSH) b4[kk] = *reinterpret_cast<const float4*>(bp + (k0 + kk) * ldb);
         else b4[kk] = __ldg(reinterpret_cast<const float4*>(bp + (k0 + kk) * ldb));
       }
 #pragma unroll
       for (int i = 0; i < TM; ++i) {
-        const float4 a4 = lds4(ar[i] + (uint32_t)k0 * 4u);
+        const float4 a4 = *reinterpret_cast<const float4*>(ar[i] + k0);
         float2 a2;
         a2 = make_float2(a4.x, a4.x);
         c2[i][0] = __ffma2_rn(a2, make_float2(b4[0].x, b4[0].y), c2[i][0]); c2[i][1] = __ffma2_rn(a2, make_float2(b4[0].z, b4[0].w), c2[i][1]);
@@ -92,10 +90,10 @@ __device__ __noinline__ void gemm_nn_impl(const float* __restrict__ A, int lda, 
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
       if (r0 + i < M) {
-        const uint32_t p = Cs + (uint32_t)((r0 + i) * ldc + n0) * 4u;
+        float4* p = reinterpret_cast<float4*>(C + (r0 + i) * ldc + n0);
         float4 v = make_float4(c2[i][0].x, c2[i][0].y, c2[i][1].x, c2[i][1].y);
-        if (acc) { const float4 o = lds4(p); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-        sts4(p, v);
+        if (acc) { const float4 o = *p; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+        *p = v;
       }
     }
   }
@@ -104,50 +102,72 @@ __device__ __noinline__ void gemm_nn_impl(const float* __restrict__ A, int lda, 
 
 // column sums with up to four weights per row:
 //   out[(ldo > 0 ? e * ldo : e * N) + n] += sum_r Wt[r][e] * Mat[r * ldm + n]   (e < 4; Wt == nullptr: plain sum, e = 0)
-// thread = (column n, row group g of G = NT / N); groups are combined through the scratch in group order.
+// thread = (column n, row group g of G = NT / N).  Narrow matrices (N = 1, 4, ...: loss sums, grad b_out) have many
+// groups inside one warp: those are combined by shuffles first, so that the second stage adds at most NT / 32 partials
+// per output (summing 256 partials in one thread cost more than the sums themselves).  Fixed order throughout.
 __device__ __noinline__ void wcolsum_impl(const float* __restrict__ Mat_, int ldm, int N, const float* __restrict__ Wt_, int M, float* out,
-                                          bool out_shared, int ldo, float* scratch_) {
-  const float* Mat = Mat_; const float* Wt = Wt_; float* scratch = scratch_;
-  __builtin_assume(__isShared(Mat)); __builtin_assume(__isShared(scratch));
-  if (Wt) __builtin_assume(__isShared(Wt));
+                                          int ldo, float* scratch_) {
+  const float* Mat = shp(Mat_);
+  const float* Wt = Wt_ ? shp(Wt_) : nullptr;
+  float* scratch = shp(scratch_);
   const int NE = Wt ? 4 : 1;
+  const int tid = threadIdx.x;
+  const bool narrow = N < 32 && (32 % N) == 0;
   int G = NT / N;
-  if (G * NE * N > SCRATCH_FLOATS) G = SCRATCH_FLOATS / (NE * N);
-  if (G > M) G = M > 0 ? M : 1;
-  const int tid = threadIdx.x, n = tid % N, g = tid / N;
+  if (!narrow && G * NE * N > SCRATCH_FLOATS) G = SCRATCH_FLOATS / (NE * N);
+  const int n = tid % N, g = tid / N;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   if (g < G) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int r = g; r < M; r += G) {
-      const float v = Mat[r * ldm + n];
-      if (Wt) {
-        const float4 w = lds4(saddr(Wt + r * 4));
+    if (Wt) {
+#pragma unroll 4
+      for (int r = g; r < M; r += G) {
+        const float v = Mat[r * ldm + n];
+        const float4 w = *reinterpret_cast<const float4*>(Wt + r * 4);
         a0 = fmaf(w.x, v, a0); a1 = fmaf(w.y, v, a1); a2 = fmaf(w.z, v, a2); a3 = fmaf(w.w, v, a3);
-      } else {
-        a0 += v;
+      }
+    } else {
+#pragma unroll 4
+      for (int r = g; r < M; r += G) a0 += Mat[r * ldm + n];
+    }
+  }
+  int Gs = G;   // partials per output that reach the scratch
+  if (narrow) {   // the 32 / N groups of a warp -> one partial per warp (whole warps: NT is a multiple of 32)
+    for (int off = N; off < 32; off <<= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+      if (Wt) {
+        a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+        a3 += __shfl_xor_sync(0xffffffffu, a3, off);
       }
     }
+    Gs = NT / 32;
+    if ((tid & 31) < N) {
+      float* s = scratch + ((tid >> 5) * NE) * N + n;
+      s[0] = a0;
+      if (Wt) { s[N] = a1; s[2 * N] = a2; s[3 * N] = a3; }
+    }
+  } else if (g < G) {
     float* s = scratch + (g * NE) * N + n;
     s[0] = a0;
     if (Wt) { s[N] = a1; s[2 * N] = a2; s[3 * N] = a3; }
   }
   __syncthreads();
-  float* outp = out;
   for (int i = tid; i < NE * N; i += NT) {
     float t = 0.f;
-    for (int q = 0; q < G; ++q) t += scratch[q * NE * N + i];
+    for (int q = 0; q < Gs; ++q) t += scratch[q * NE * N + i];
     const int e = i / N, c = i - e * N;
-    outp[(ldo > 0 ? e * ldo : e * N) + c] += t;
+    out[(ldo > 0 ? e * ldo : e * N) + c] += t;
   }
   __syncthreads();
 }
 
 // out[N, Kd] += A^T S over the tile's M rows.  4 x 4 register tiles over (n, kd); when there are fewer tiles than
 // threads the rows are split over thread groups that are combined through the scratch in group order.
-__device__ __noinline__ void gemm_tn_impl(const float* __restrict__ A_, int lda, const float* __restrict__ S_, int lds, float* out, bool out_shared,
-                                          int N, int Kd, int M, float* scratch_) {
-  float* scratch = scratch_; float* outp = out;
-  __builtin_assume(__isShared(scratch));
-  const uint32_t As = saddr(A_), Ss = saddr(S_);
+__device__ __noinline__ void gemm_tn_impl(const float* __restrict__ A_, int lda, const float* __restrict__ S_, int lds, float* out, int N, int Kd,
+                                          int M, float* scratch_) {
+  const float* A = shp(A_);
+  const float* S = shp(S_);
+  float* scratch = shp(scratch_);
   const int nkg = Kd >> 2, ntiles = (N >> 2) * nkg;
   int G = NT / ntiles;
   if (G < 1) G = 1;
@@ -162,12 +182,13 @@ __device__ __noinline__ void gemm_tn_impl(const float* __restrict__ A_, int lda,
 #pragma unroll
     for (int i = 0; i < 4; ++i) { c2[i][0] = make_float2(0.f, 0.f); c2[i][1] = make_float2(0.f, 0.f); }
     if (live) {
-      uint32_t ap = As + (uint32_t)(g * lda + n0) * 4u, sq = Ss + (uint32_t)(g * lds + k0) * 4u;
-      const uint32_t astep = (uint32_t)(G * lda) * 4u, sstep = (uint32_t)(G * lds) * 4u;
+      const float* ap = A + g * lda + n0;
+      const float* sq = S + g * lds + k0;
+      const int astep = G * lda, sstep = G * lds;
 #pragma unroll 4
       for (int m = g; m < M; m += G) {
-        const float4 a = lds4(ap);
-        const float4 s = lds4(sq);
+        const float4 a = *reinterpret_cast<const float4*>(ap);
+        const float4 s = *reinterpret_cast<const float4*>(sq);
         ap += astep; sq += sstep;
         const float2 slo = make_float2(s.x, s.y), shi = make_float2(s.z, s.w);
         float2 a2;
@@ -188,10 +209,10 @@ __device__ __noinline__ void gemm_tn_impl(const float* __restrict__ A_, int lda,
       for (int i = 0; i < 4; ++i) {
         float4 v = make_float4(c2[i][0].x, c2[i][0].y, c2[i][1].x, c2[i][1].y);
         for (int q = 1; q < G; ++q) {
-          const float4 o = lds4(saddr(scratch + (q - 1) * N * Kd + (n0 + i) * Kd + k0));
+          const float4 o = *reinterpret_cast<const float4*>(scratch + (q - 1) * N * Kd + (n0 + i) * Kd + k0);
           v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
         }
-        float4* p = reinterpret_cast<float4*>(outp + (n0 + i) * Kd + k0);
+        float4* p = reinterpret_cast<float4*>(out + (n0 + i) * Kd + k0);   // accumulators: shared memory or an L2 slot
         const float4 o = *p;
         v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
         *p = v;
@@ -202,44 +223,34 @@ __device__ __noinline__ void gemm_tn_impl(const float* __restrict__ A_, int lda,
   __syncthreads();
 }
 
-// u[r][m] = S[r, :] . W[m, :] (+ b[m] on value rows); four lanes per row (a quarter of the units each, starting
-// bank rotated by the row so that the eight rows of a warp hit different banks), combined by shuffles
-__device__ __noinline__ void rowdot_impl(const float* __restrict__ S_, int lds, const float* __restrict__ W, const float* __restrict__ b, float* U_, int M,
+// u[r][m] = S[r, :] . W[m, :] (+ b[m] on value rows).  One thread per (row, output): the row and the weight row are
+// read as float4 pieces starting at a lane-dependent column (a quarter warp then touches 8 different 16-byte columns
+// of its 8 rows: conflict-free) with every load issued before the first FMA.
+template <bool WSH>
+__device__ __noinline__ void rowdot_impl(const float* __restrict__ S_, int lds, const float* __restrict__ W_, const float* __restrict__ b, float* U_, int M,
                                          int Hp, int o, int C) {
-  const float* S = S_; float* U = U_;
-  __builtin_assume(__isShared(S)); __builtin_assume(__isShared(U));
-  const int q4 = Hp >> 2;
-  for (int t0 = 0; t0 < 4 * M; t0 += NT) {   // whole warps iterate together (shuffles below)
-    const int t = t0 + threadIdx.x;
-    const int r = t >> 2, part = t & 3;
-    const bool live = r < M;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (live) {
-      const float* s = S + r * lds + part * q4;
-      const float* w = W + part * q4;
-      int j = (r >> 3) & (q4 - 1);   // q4 is a power of two (Hp = 32, 64)
-      for (int q = 0; q < q4; ++q) {
-        const float sv = s[j];
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-          if (m < o) acc[m] = fmaf(sv, w[m * Hp + j], acc[m]);
-        j = (j + 1) & (q4 - 1);
+  const float* S = shp(S_);
+  float* U = shp(U_);
+  const float* W = WSH ? shp(W_) : W_;
+  for (int t = threadIdx.x; t < M * 4; t += NT) {
+    const int r = t >> 2, m = t & 3;
+    float acc = 0.f;
+    if (m < o) {
+      const float* s = S + r * lds;
+      const float* w = W + m * Hp;
+      const int rot = ((t >> 2) & 7) * 4;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+      for (int q = 0; q < Hp; q += 4) {
+        const int j = (rot + q) & (Hp - 1);   // Hp = 32 or 64
+        const float4 sv = *reinterpret_cast<const float4*>(s + j);
+        const float4 wv = WSH ? *reinterpret_cast<const float4*>(w + j) : __ldg(reinterpret_cast<const float4*>(w + j));
+        a0 = fmaf(sv.x, wv.x, a0); a1 = fmaf(sv.y, wv.y, a1); a2 = fmaf(sv.z, wv.z, a2); a3 = fmaf(sv.w, wv.w, a3);
       }
+      acc = (a0 + a1) + (a2 + a3);
+      if ((r % C) == 0) acc += b[m];
     }
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], 1);
-      acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], 2);
-    }
-    if (live && part == 0) {
-      const bool vrow = (r % C) == 0;
-      float4 out;
-      out.x = acc[0] + (vrow ? b[0] : 0.f);
-      out.y = (1 < o) ? acc[1] + (vrow ? b[1] : 0.f) : 0.f;
-      out.z = (2 < o) ? acc[2] + (vrow ? b[2] : 0.f) : 0.f;
-      out.w = (3 < o) ? acc[3] + (vrow ? b[3] : 0.f) : 0.f;
-      sts4(saddr(U + r * 4), out);
-    }
+    U[r * 4 + m] = acc;
   }
   __syncthreads();
 }
@@ -323,18 +334,19 @@ struct TileBackend {
   }
   __device__ __forceinline__ void wcolsum_acc(const float* Mat, int64_t ldm, int N, const float* Wt, int64_t M, float* out, float*, int64_t,
                                               int64_t ldo = 0) {
-    wcolsum_impl(Mat, (int)ldm, N, Wt, (int)M, out, g_shared, (int)ldo, scratch);
+    wcolsum_impl(Mat, (int)ldm, N, Wt, (int)M, out, (int)ldo, scratch);
     stamp(4);
   }
   // (+ outE[e * ldoE + n] += sum_m A[m, n] E[m, e]: grad[U | b] = Abar^T E)
   __device__ __forceinline__ void gemm_tn_acc(const float* A, int64_t lda, const float* S, int64_t lds, float* out, int N, int Kd, int64_t M,
                                               const float* E, float* outE, int64_t ldoE, float*, int64_t) {
-    gemm_tn_impl(A, (int)lda, S, (int)lds, out, g_shared, N, Kd, (int)M, scratch);
+    gemm_tn_impl(A, (int)lda, S, (int)lds, out, N, Kd, (int)M, scratch);
     stamp(5);
-    if (E) { wcolsum_impl(A, (int)lda, N, E, (int)M, outE, g_shared, (int)ldoE, scratch); stamp(6); }
+    if (E) { wcolsum_impl(A, (int)lda, N, E, (int)M, outE, (int)ldoE, scratch); stamp(6); }
   }
   __device__ __forceinline__ void rowdot(const float* S, int64_t lds, const float* W, const float* b, float* U, int64_t M, int Hp, int o, int C) {
-    rowdot_impl(S, (int)lds, W, b, U, (int)M, Hp, o, C);
+    if (w_shared) rowdot_impl<true>(S, (int)lds, W, b, U, (int)M, Hp, o, C);
+    else rowdot_impl<false>(S, (int)lds, W, b, U, (int)M, Hp, o, C);
     stamp(7);
   }
   __device__ __forceinline__ void zero(void* p, size_t bytes) {
@@ -348,8 +360,7 @@ struct TileBackend {
 // shared memory: [scratch][weights if w_smem][accumulators if g_smem][Lp][tile region]
 template <int PROB, class BK>
 __global__ void __launch_bounds__(NT, 1) tile_step_kernel(const __grid_constant__ TileParams prm) {
-  extern __shared__ __align__(16) float smem[];
-  float* sp = smem;
+  float* sp = g_tile_smem;
   BK bk;
   bk.scratch = sp; sp += SCRATCH_FLOATS;
   bk.hl_stride = 0;
