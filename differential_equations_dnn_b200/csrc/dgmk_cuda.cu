@@ -594,11 +594,11 @@ struct CudaBackend : BackendTraitsAll {
   // Plans the shared-memory layout, launches the kernel on c.Wp (packed) and adds the per-CTA partials into c.Gp.
   // false = shape not covered (the caller runs the layer-wise path).
   // shared-memory budget left for the tile region after the fixed parts (scratch, staged weights, accumulators)
-  int64_t tile_fixed(const Ctx& c, tk::TileParams& prm) {
+  int64_t tile_fixed(const Ctx& c, tk::TileParams& prm, int64_t smem_limit = tk::SMEM_MAX) {
     prm.n = c.n; prm.pl = c.pl; prm.Wp = c.Wp; prm.slots = c.part;
     prm.w_floats = (uint32_t)((c.pl.w_total + 3) / 4 * 4);
     prm.g_floats = (uint32_t)c.pl.g_total;
-    int64_t budget = tk::SMEM_MAX - (int64_t)tk::SCRATCH_FLOATS * 4;
+    int64_t budget = smem_limit - (int64_t)tk::SCRATCH_FLOATS * 4;
     prm.w_smem = (int64_t)prm.w_floats * 4 <= 64 * 1024;
     if (prm.w_smem) budget -= (int64_t)prm.w_floats * 4;
     prm.g_smem = (int64_t)prm.g_floats * 4 <= 32 * 1024;
@@ -611,14 +611,17 @@ struct CudaBackend : BackendTraitsAll {
   // grid / slot bookkeeping, launch, second-stage reduction of the per-CTA partials into c.Gp
   bool tile_launch(Ctx& c, int prob, tk::TileParams& prm, double falg, double balg) {
     const int64_t ntiles = (prm.B + prm.P - 1) / prm.P;
-    const int64_t grid = ntiles < sms ? ntiles : sms;
+    const size_t smem_need = (size_t)tk::SCRATCH_FLOATS * 4 + (prm.w_smem ? (size_t)prm.w_floats * 4 : 0) + (prm.g_smem ? (size_t)prm.g_floats * 4 : 0) +
+                             ((size_t)prm.lp_floats + prm.coord_floats + prm.ip_floats) * 4 + prm.tile_bytes;
+    // two CTAs per SM when the plan fits half an SM's shared memory (the kernels that allow it are compiled for it)
+    const int64_t ctas = (int64_t)sms * ((prob != tk::PROB_HEAT && smem_need <= (size_t)tk::SMEM_HALF) ? 2 : 1);
+    const int64_t grid = ntiles < ctas ? ntiles : ctas;
     const int64_t slots_avail = c.part_n / prm.g_floats;
     if (slots_avail < grid) return false;
     int64_t nseg = ((ntiles + grid - 1) / grid + tk::FLUSH_TILES - 1) / tk::FLUSH_TILES;
     if (nseg * grid > slots_avail) nseg = slots_avail / grid;
     prm.nslots_per_cta = (int32_t)nseg;
-    const size_t smem = (size_t)tk::SCRATCH_FLOATS * 4 + (prm.w_smem ? (size_t)prm.w_floats * 4 : 0) + (prm.g_smem ? (size_t)prm.g_floats * 4 : 0) +
-                        ((size_t)prm.lp_floats + prm.coord_floats + prm.ip_floats) * 4 + prm.tile_bytes;
+    const size_t smem = smem_need;
     note(cudaMemsetAsync(c.part, 0, (size_t)grid * nseg * prm.g_floats * 4, st));
     {
       ProfScope ps(PC_TILE, st, falg, balg);
@@ -633,14 +636,22 @@ struct CudaBackend : BackendTraitsAll {
   bool tile_step(Ctx& c, int cls, const HeatArgs* ha, const OdeArgs* oa, int64_t B) {
     if (!g_tile || c.n.Hp > TILE_MAX_HP || B <= 0) return false;
     tk::TileParams prm;
-    const int64_t budget = tile_fixed(c, prm);
-    prm.B = B;
     // per-point extras: loss contribution per loss row + the staged coordinates of the larger pass
     auto coord_fl = [&](int64_t P) { return r4((cls == DGMK_WS_HEAT ? 6 : 1) * P); };
     auto need = [&](int64_t P) { return (int64_t)chunk_region_bytes(c.n, cls, P, 0, true) + r4(loss_points(cls, P, 0)) * 4 + coord_fl(P) * 4; };
-    int64_t P = 0;
     const int64_t Pcap = B < 128 ? B : 128;
-    for (int64_t q = 1; q <= Pcap; ++q) { if (need(q) <= budget) P = q; else break; }
+    auto plan = [&](int64_t limit) {
+      const int64_t budget = tile_fixed(c, prm, limit);
+      int64_t P = 0;
+      for (int64_t q = 1; q <= Pcap; ++q) { if (need(q) <= budget) P = q; else break; }
+      return P;
+    };
+    // Two CTAs per SM hide each other's stage barriers (simple_ode MLP(1,1,32): 4.5e8 -> 5.0e8 rows/s) as long as a
+    // half-SM tile still has >= 128 interior rows; smaller tiles lose more than the overlap gains (measured: heat
+    // DGM(2,1,32,1) 15.7 -> 24.2 ms with 11-point tiles), and the heat kernels are compiled for one CTA per SM.
+    int64_t P = (cls == DGMK_WS_HEAT) ? 0 : plan(tk::SMEM_HALF);
+    if (P * 2 < 128 && P < B) P = plan(tk::SMEM_MAX);
+    prm.B = B;
     if (P < 2 && P < B) return false;
     // Measured crossover (tools/tile_sweep.py): with the whole stash in shared memory the tiles of wide / deep
     // networks get small (7 heat points at hidden size 64, 3 layers) and past a few thousand rows the layer-wise

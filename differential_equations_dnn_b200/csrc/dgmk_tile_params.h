@@ -9,8 +9,9 @@ namespace tk {
 
 constexpr int NT = 256;                 // threads per CTA, one CTA per SM (measured: 512 threads 19.3 ms, 1024 25.4 ms, 256 16.2 ms
                                         // per 2^20 heat rows at hidden size 32 -- fewer idle lanes at the stage barriers, no spills)
-constexpr int SCRATCH_FLOATS = 4096;    // cross-group reduction scratch (16 KB)
+constexpr int SCRATCH_FLOATS = 2048;    // cross-group reduction scratch (8 KB)
 constexpr int SMEM_MAX = 232448;        // 227 KB opt-in limit per CTA on sm_100
+constexpr int SMEM_HALF = 115712;       // two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2
 constexpr int FLUSH_TILES = 256;        // tiles per FP32 accumulation segment
 
 enum { PROB_HEAT = 0, PROB_ODE = 1, PROB_FRED = 2 };   // ODE covers simple_ode and FitzHugh-Nagumo (OdeArgs::fhn)
