@@ -67,6 +67,7 @@ _CUDA_ONLY = {
     "dgmk_set_gemm_engine": (None, [C.c_int]),
     "dgmk_set_tile_engine": (None, [C.c_int]),
     "dgmk_tile_profile": (None, [_P, C.c_int]),
+    "dgmk_set_tile_flush": (None, [C.c_int]),
     "dgmk_profile": (None, [C.c_int]),
     "dgmk_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double),
                                     C.POINTER(C.c_double)]),

@@ -29,6 +29,7 @@ static bool g_fuse = true;
 static int g_tile = 1;   // 0 off, 1 on where it wins (dispatch rule in tile_step), 2 forced on wherever it fits
 static long long* g_tile_prof = nullptr;   // dgmk_tile_profile: device buffer for CTA 0's stage timeline
 static int g_tile_prof_n = 0;
+static int g_tile_flush = tk::FLUSH_TILES;   // dgmk_set_tile_flush (tests: several accumulation segments on small batches)
 namespace tk { int launch(int prob, const TileParams& prm, int grid, size_t smem, void* stream); }   // dgmk_tile.cu
 
 // ---- per-kernel-class timing (dgmk_profile*): CUDA events recorded on the launch stream around
@@ -618,9 +619,10 @@ struct CudaBackend : BackendTraitsAll {
     const int64_t grid = ntiles < ctas ? ntiles : ctas;
     const int64_t slots_avail = c.part_n / prm.g_floats;
     if (slots_avail < grid) return false;
-    int64_t nseg = ((ntiles + grid - 1) / grid + tk::FLUSH_TILES - 1) / tk::FLUSH_TILES;
+    int64_t nseg = ((ntiles + grid - 1) / grid + g_tile_flush - 1) / g_tile_flush;
     if (nseg * grid > slots_avail) nseg = slots_avail / grid;
     prm.nslots_per_cta = (int32_t)nseg;
+    prm.flush_tiles = g_tile_flush;
     const size_t smem = smem_need;
     note(cudaMemsetAsync(c.part, 0, (size_t)grid * nseg * prm.g_floats * 4, st));
     {
@@ -782,6 +784,9 @@ void dgmk_set_tile_engine(int on) { dgmk::g_tile = on; }
 // diagnostic: CTA 0 of the following resident-tile launches writes (clock64, stage kind) pairs -- one per stage, at most
 // n -- into buf (device memory, 2 * n int64); kinds: 0 start, 1 ew, 2 ew4, 3 gemm_nn, 4 column sums, 5 gemm_tn, 6 A^T E,
 // 7 rowdot.  buf = NULL switches it off.
+// tiles per FP32 accumulation segment of the resident-tile step (default 256; tests lower it to exercise the segment
+// hand-over on small batches)
+void dgmk_set_tile_flush(int tiles) { dgmk::g_tile_flush = tiles > 0 ? tiles : dgmk::tk::FLUSH_TILES; }
 void dgmk_tile_profile(long long* buf, int n) { dgmk::g_tile_prof = buf; dgmk::g_tile_prof_n = buf ? n : 0; }
 // same tcgen05 tile the pipeline launches: C[M,N] = A[M,K] Bt[N,K]^T, lda = ldc = ld
 int dgmk_gemm_tc_probe(const float* A, const float* Bt, float* C, int64_t M, int N, int K, int64_t ld, void* stream) {

@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(NT, PROB == PROB_HEAT ? 1 : 2) tile_step_kerne
     if (PROB == PROB_HEAT) heat_chunk(pipe, cv, 0, prm.heat, p0, r);
     else if (PROB == PROB_ODE) ode_like_chunk(pipe, cv, 0, prm.ode, p0, r);
     else fredholm_block(pipe, cv, 0, prm.fred, p0, r, prm.J, Ip);
-    if (++in_seg == FLUSH_TILES && slot + 1 < prm.nslots_per_cta) {   // start a new FP32 accumulation segment
+    if (++in_seg == prm.flush_tiles && slot + 1 < prm.nslots_per_cta) {   // start a new FP32 accumulation segment
       if (prm.g_smem) {
         float* dst = slot0 + (size_t)slot * prm.g_floats;
         for (uint32_t i = tid; i < prm.g_floats; i += NT) { dst[i] = gsm[i]; gsm[i] = 0.f; }

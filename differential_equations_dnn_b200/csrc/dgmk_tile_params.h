@@ -23,6 +23,7 @@ struct TileParams {
   int64_t B;              // points of this launch
   int32_t P;              // points per tile
   int32_t nslots_per_cta;
+  int32_t flush_tiles;    // tiles per FP32 accumulation segment (FLUSH_TILES; a diagnostic knob lowers it in tests)
   int32_t w_smem, g_smem; // stage the weights / keep the accumulators in shared memory
   uint32_t w_floats, g_floats, lp_floats, coord_floats, ip_floats, tile_bytes;
   int32_t J;              // Fredholm: quadrature nodes per sub-tile (rows per sub-tile = P * J)

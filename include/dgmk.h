@@ -146,6 +146,8 @@ void dgmk_set_gemm_engine(int engine);
 void dgmk_set_tile_engine(int on);
 /* stage timeline of CTA 0 of the resident-tile kernel: (clock64, stage kind) pairs into buf (device, 2 * n int64) */
 void dgmk_tile_profile(long long* buf, int n);
+/* tiles per FP32 accumulation segment of the resident-tile step (default 256; <= 0 restores it) */
+void dgmk_set_tile_flush(int tiles);
 /* Per-kernel-class timing with CUDA events on the launch stream.  dgmk_profile(1) clears and
  * starts, dgmk_profile(0) stops; dgmk_profile_read synchronises the recorded events and returns the
  * class's summed duration [ms], launches, ALGORITHMIC flops and bytes.  Classes: 0 weight gradient,

@@ -270,3 +270,71 @@ def test_engines_agree(K, kind, prob):
         for off, n, live in grad_groups([(off, n, live) for _, off, n, live in net.param_slices()]):
             if live and np.linalg.norm(go[off:off + n]) > 0:
                 assert rel(out[eng][off:off + n], go[off:off + n]) < tol, (eng, off, rel(out[eng][off:off + n], go[off:off + n]))
+
+
+# ------------------------------------------------------------------------------------------------
+# The resident-tile step (csrc/dgmk_tile.cuh: one persistent kernel per step for hidden sizes <= 64) against the
+# layer-wise path and the FP64 oracle: many tiles per CTA, ragged last tile, several FP32 accumulation segments,
+# weights / accumulators in shared memory (hidden size 32) and in L2 (hidden size 64, 3 layers), one and two CTAs per SM.
+@pytest.mark.parametrize("case", ["heat_dgm32", "heat_dgm64x3", "heat_mlp64", "ode_mlp32", "fhn_dgm32", "fredholm_dgmraw32", "fredholm_k70"])
+def test_tile_step_vs_layerwise_and_oracle(K, case):
+    from differential_equations_dnn_b200 import _cabi, dgm_net, neural_networks
+    from oracle import jets_np
+    lib = _cabi.load()
+    torch.manual_seed(3)
+    gen = torch.Generator().manual_seed(4)
+    if case.startswith("heat"):
+        B = 5000 + 13
+        net = {"heat_dgm32": lambda: dgm_net.DGM(2, 1, 32, 1), "heat_dgm64x3": lambda: dgm_net.DGM(2, 1, 64, 3),
+               "heat_mlp64": lambda: neural_networks.MLP(2, 1, 50, 2, activation="sigmoid")}[case]().cuda()
+        x = torch.pi * torch.rand([B, 1], generator=gen); t = 3.0 * torch.rand([B, 1], generator=gen); z = torch.zeros(B, 1)
+        host = [torch.cat([x, t], 1), torch.cat([x, z], 1), torch.cat([z, t], 1), torch.cat([z + torch.pi, t], 1), z, z.clone()]
+        fn, ofn = K.heat_step, jets_np.heat_step
+    elif case == "ode_mlp32":
+        B = 40000 + 7
+        net = neural_networks.MLP(1, 1, 32, 1, activation="tanh").cuda()
+        host = [1.01 * torch.rand([B, 1], generator=gen), torch.zeros(B, 1), 2.0 * torch.ones(B, 1)]
+        fn, ofn = K.ode_step, jets_np.ode_step
+    elif case == "fhn_dgm32":
+        B = 9000 + 1
+        net = dgm_net.DGM(1, 2, 32, 2).cuda()
+        host = [30.01 * torch.rand([B, 1], generator=gen), torch.zeros(B, 1), torch.zeros(B, 2)]
+        fn, ofn = K.fhn_step, jets_np.fhn_step
+    else:
+        B, k = (300 + 5, 50) if case == "fredholm_dgmraw32" else (37, 70)
+        net = neural_networks.DGM(1, 1, 32, 1).cuda()
+        with torch.no_grad():   # off the exact ReLU ties of the zero-initialised biases
+            net.flat_theta().add_(0.01 * torch.randn(net.flat_theta().shape, generator=gen).cuda())
+        host = [(np.pi / 2) * torch.rand([B, 1], generator=gen), (np.pi / 2) * torch.rand([k, B, 1], generator=gen)]
+        fn, ofn = K.fredholm_step, jets_np.fredholm_step
+    args = [a.cuda() for a in host]
+    d = net.desc
+    spec = np.array([d.kind, d.input_dim, d.output_dim, d.hidden_size, d.num_layers, d.activation])
+    lo, go = ofn(spec, net.flat_theta().double().cpu().numpy(), *[a.double().numpy() for a in host])
+    out = {}
+    try:
+        for tag, eng, flush in (("tile", 2, 0), ("tile_segments", 2, 2), ("layerwise", 0, 0)):
+            lib.dgmk_set_tile_engine(eng)
+            lib.dgmk_set_tile_flush(flush)
+            n0 = lib.dgmk_launch_count()
+            out[tag] = fn(d, net.flat_theta(), *args).double().cpu().numpy()
+            launches = lib.dgmk_launch_count() - n0
+            assert (launches <= 5) == tag.startswith("tile"), (tag, launches)   # pack + tile kernel + reduce + unpack
+    finally:
+        lib.dgmk_set_tile_engine(1)
+        lib.dgmk_set_tile_flush(0)
+    layout = grad_groups([(off, n, live) for _, off, n, live in net.param_slices()])
+    relu = "dgmraw" in case or case == "fredholm_k70"
+    tol = 3e-5 if relu else TOL   # ReLU: rows within rounding of a kink flip in any FP32 evaluation (see test_engines_agree)
+    for tag, o in out.items():
+        assert abs(o[-1] - lo) <= tol * abs(lo), (tag, o[-1], lo)
+        for off, n, live in layout:
+            if live and np.linalg.norm(go[off:off + n]) > 0:
+                assert rel(o[off:off + n], go[off:off + n]) < tol, (tag, off, rel(o[off:off + n], go[off:off + n]))
+    # the tile step is deterministic: same launch twice -> same bits
+    lib.dgmk_set_tile_engine(2)
+    try:
+        again = fn(d, net.flat_theta(), *args).double().cpu().numpy()
+    finally:
+        lib.dgmk_set_tile_engine(1)
+    assert np.array_equal(again, out["tile"])
