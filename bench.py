@@ -547,7 +547,7 @@ def driver_latency(pk, wl, dev):
     """The reference's own regime: its training driver at the SHIPPED batch size (heat.py / simple_ode.py:
     64 rows, fitzhugh_nagumo.py: 100, fredholm.py: 32 rows x k = 50) is launch-bound.  us per iteration of this package's
     `minimize_loss_dgm` for the workload's network -- sampler, fused step, Adam, loss record -- launched from Python
-    (eager) and replayed from a CUDA graph (cuda_graph=True; capture cost excluded by differencing two run lengths)."""
+    (eager; difference of two run lengths) and replayed from a CUDA graph (cuda_graph=True; CUDA events around the replays)."""
     import contextlib
     import io
     rows = {"heat": 64, "ode": 64, "fhn": 100, "fredholm": 32}[wl.name]
@@ -571,11 +571,13 @@ def driver_latency(pk, wl, dev):
     try:
         run(30, False), run(30, True)   # warm the caches both modes rely on
         eager = (run(330, False) - run(30, False)) / 300
-        graph = (run(1230, True) - run(230, True)) / 1000
+        run(1011, True)                 # CUDA events around the 1000 replays (_loop.last_timing): capture excluded
+        lt = pk._loop.last_timing
+        graph = lt["ms"] * 1e-3 / max(lt["replays"], 1)
         return {"rows": rows, "k": 50 if wl.name == "fredholm" else None, "eager_us_per_iteration": eager * 1e6,
                 "cuda_graph_us_per_iteration": graph * 1e6,
                 "what": "this package's minimize_loss_dgm at the reference driver's shipped batch size (sampler + fused step + "
-                        "fused Adam + loss record per iteration); differences of two run lengths, capture excluded"}
+                        "fused Adam + loss record per iteration); eager: difference of two run lengths, graph: CUDA events around 1000 replays"}
     except Exception as e:
         return {"error": repr(e)}
 

@@ -8,6 +8,9 @@ it.  Same RNG stream and arithmetic as the eager loop; losses stay on the device
 """
 import torch
 
+# timing of the last graphed_loop call: {"replays": n, "ms": CUDA-event time of the n replays} (bench.py's driver latency)
+last_timing = {"replays": 0, "ms": 0.0}
+
 
 def graphed_loop(step, iterations, device, warmup=11):
     """step() -> 0-dim loss tensor; it must do its own zero_grad / backward / optimizer.step with
@@ -32,8 +35,15 @@ def graphed_loop(step, iterations, device, warmup=11):
         with torch.cuda.graph(graph, stream=side):
             one_iteration()
         # the capture itself does not execute: iteration n_eager is the first replay
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         for _ in range(iterations - n_eager):
             graph.replay()
+        e1.record()
+        out = losses[:iterations].cpu().tolist()   # synchronises
+        last_timing.update(replays=iterations - n_eager, ms=e0.elapsed_time(e1))
+        return out
+    last_timing.update(replays=0, ms=0.0)
     return losses[:iterations].cpu().tolist()
 
 

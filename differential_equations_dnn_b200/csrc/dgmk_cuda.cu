@@ -599,7 +599,7 @@ struct CudaBackend : BackendTraitsAll {
     prm.n = c.n; prm.pl = c.pl; prm.Wp = c.Wp; prm.slots = c.part;
     prm.w_floats = (uint32_t)((c.pl.w_total + 3) / 4 * 4);
     prm.g_floats = (uint32_t)c.pl.g_total;
-    int64_t budget = smem_limit - (int64_t)tk::SCRATCH_FLOATS * 4;
+    int64_t budget = smem_limit - (int64_t)tk::SCRATCH_TOTAL_FLOATS * 4;
     prm.w_smem = (int64_t)prm.w_floats * 4 <= 64 * 1024;
     if (prm.w_smem) budget -= (int64_t)prm.w_floats * 4;
     prm.g_smem = (int64_t)prm.g_floats * 4 <= 32 * 1024;
@@ -612,7 +612,7 @@ struct CudaBackend : BackendTraitsAll {
   // grid / slot bookkeeping, launch, second-stage reduction of the per-CTA partials into c.Gp
   bool tile_launch(Ctx& c, int prob, tk::TileParams& prm, double falg, double balg) {
     const int64_t ntiles = (prm.B + prm.P - 1) / prm.P;
-    const size_t smem_need = (size_t)tk::SCRATCH_FLOATS * 4 + (prm.w_smem ? (size_t)prm.w_floats * 4 : 0) + (prm.g_smem ? (size_t)prm.g_floats * 4 : 0) +
+    const size_t smem_need = (size_t)tk::SCRATCH_TOTAL_FLOATS * 4 + (prm.w_smem ? (size_t)prm.w_floats * 4 : 0) + (prm.g_smem ? (size_t)prm.g_floats * 4 : 0) +
                              ((size_t)prm.lp_floats + prm.coord_floats + prm.ip_floats) * 4 + prm.tile_bytes;
     // two CTAs per SM when the plan fits half an SM's shared memory (the kernels that allow it are compiled for it)
     const int64_t ctas = (int64_t)sms * ((prob != tk::PROB_HEAT && smem_need <= (size_t)tk::SMEM_HALF) ? 2 : 1);

@@ -137,6 +137,13 @@ inline size_t ctx_bytes(const NetDims& n, const PackedLayout& pl, int64_t max_po
 // the run-time switches below compile to the one live branch.
 struct BackendTraitsAll {
   static constexpr bool kHasTile = false;   // resident-tile step (dgmk_tile.cuh): CUDA backend only
+  // Stage grouping (resident-tile step: a stage boundary is a CTA barrier that costs ~2000 cycles of a ~45000-cycle
+  // pass, profiles/r02_tile_timeline.txt).  Between nosync(true) and nosync(false) the element-wise / gemm_nn calls of
+  // a backend that groups do NOT end in a barrier: the orchestration brackets only stages that neither read what an
+  // earlier stage of the bracket writes nor write what it reads or writes, and the first stage after the bracket ends
+  // the group with its own barrier.  Host-launched backends (stream order) ignore it.
+  static constexpr bool kGroupsStages = false;
+  DGMK_HD void nosync(bool) {}
   DGMK_HD bool inplace_rev() const { return false; }   // reverse pass overwrites the stash (carve_rev)
   // hook: a backend may copy the `rows` coordinate rows a pass reads to faster memory and re-point xs at the copy
   DGMK_HD void stage_coords(XSrc&, int64_t) const {}
@@ -218,7 +225,9 @@ struct Pipeline {
       const double unit = 4.0 * (double)M * Hp;   // one [M, Hp] FP32 matrix
       ExtInputFn<CS> fe; fe.xs = pb.xs; fe.E = pb.E;
       bk.note_bytes(R * (4.0 * n.d + 16.0 * pb.C));
+      bk.nosync(true);    // E is first read by the reverse pass; the input layer reads the coordinates itself
       bk.ew(fe, R);
+      bk.nosync(false);
       DGMK_ACT_SWITCH(n.in_act(), ACT, {
         InputFwdFn<CS, ACT> f; f.xs = pb.xs; f.inb = inb(); f.S0 = pb.S[0]; f.Hp = Hp;
         bk.note_bytes(unit);
@@ -265,23 +274,33 @@ struct Pipeline {
   }
 
   // ---------------------------------------------------------------- reverse
-  // pb.UB holds the output cotangents; gradients are ACCUMULATED into c.Gp.
-  DGMK_HD_TEMPLATE void reverse(PassBufs& pb, RevBufs& rb) {
+  // pb.UB holds the output cotangents; gradients are ACCUMULATED into c.Gp.  loss_rows > 0: the pass's loss rows
+  // (c.Lp[0 .. loss_rows)) are added to the loss accumulator first (add_loss) -- a backend that groups stages does
+  // that sum, the two output-layer column sums and the output-layer adjoint in ONE stage.
+  DGMK_HD_TEMPLATE void reverse(PassBufs& pb, RevBufs& rb, int64_t loss_rows = 0) {
     const NetDims& n = c.n;
     const int Hp = n.Hp;
     const int64_t M = pb.M, R = pb.rows;
     float* Gp = c.Gp;
     const double unit = 4.0 * (double)M * Hp;
-    // output layer: grad W_out = UB^T S_L, grad b_out = sum of value-row cotangents
-    bk.wcolsum_acc(pb.S[n.L], Hp, Hp, pb.UB, M, Gp + c.pl.g_outw, c.part, c.part_n);
-    bk.wcolsum_acc(pb.UB, 4, 4, pb.E, M, Gp + c.pl.g_outb, c.part, c.part_n);
     const bool ip = bk.inplace_rev();
     float* SBn = rb.SBa;  // cotangent of the current layer's output
     float* SBp = rb.SBb;  // (in-place mode: the same buffer -- every stage reads an element before it overwrites it)
-    {
-      OutRevFn f; f.UB = pb.UB; f.outw = c.Wp + c.pl.outw; f.SB = SBn; f.Hp = Hp; f.o = n.o;
+    OutRevFn fo; fo.UB = pb.UB; fo.outw = c.Wp + c.pl.outw; fo.SB = SBn; fo.Hp = Hp; fo.o = n.o;
+    if constexpr (BK::kGroupsStages) {
+      bk.nosync(true);     // SBn is a buffer of its own: nothing the column sums read or write
+      bk.ew4(fo, M * Hp);
+      bk.nosync(false);
+      bk.wcolsum3(loss_rows > 0 ? c.Lp : nullptr, loss_rows, Gp + c.pl.g_acc,      // loss sum
+                  pb.S[n.L], Hp, pb.UB, M, Gp + c.pl.g_outw,                        // grad W_out = UB^T S_L
+                  pb.E, Gp + c.pl.g_outb);                                          // grad b_out = UB^T E
+    } else {
+      if (loss_rows > 0) add_loss(loss_rows);
+      // output layer: grad W_out = UB^T S_L, grad b_out = sum of value-row cotangents
+      bk.wcolsum_acc(pb.S[n.L], Hp, Hp, pb.UB, M, Gp + c.pl.g_outw, c.part, c.part_n);
+      bk.wcolsum_acc(pb.UB, 4, 4, pb.E, M, Gp + c.pl.g_outb, c.part, c.part_n);
       bk.note_bytes(unit + 16.0 * M);
-      bk.ew4(f, M * Hp);
+      bk.ew4(fo, M * Hp);
     }
     DGMK_CS_SWITCH(pb.cs, CS, {
       for (int l = n.L - 1; l >= 0; --l) {
@@ -292,10 +311,17 @@ struct Pipeline {
             bk.note_bytes(3 * unit);
             bk.ew(f, R * Hp);
           })
+          if constexpr (BK::kGroupsStages) {   // the data gradient (AB -> SBp) and the weight gradient (AB, S[l] -> Gp): one stage
+            bk.nosync(true);
+            bk.gemm_nn(AB, Hp, c.Wp + c.pl.wb[l], Hp, c.Wp + c.pl.wf[l], Hp, SBp, Hp, M, Hp, Hp, false);
+            bk.nosync(false);
+            bk.gemm_tn_acc(AB, Hp, pb.S[l], Hp, Gp + c.pl.g_w[l], Hp, Hp, M, pb.E, Gp + c.pl.g_ub[l], Hp, c.part, c.part_n);
+          } else {
           // grad W = Abar^T Y_prev, and grad b (row 2 of Abar^T E) in the same pass
           bk.gemm_tn_acc(AB, Hp, pb.S[l], Hp, Gp + c.pl.g_w[l], Hp, Hp, M, pb.E, Gp + c.pl.g_ub[l], Hp, c.part, c.part_n);
           if (bk.lane_ok(Hp, CS_V)) bk.lane_store(AB, Hp, c.Wp + c.pl.wf[l], SBp, Hp, Hp, M);
           else bk.gemm_nn(AB, Hp, c.Wp + c.pl.wb[l], Hp, c.Wp + c.pl.wf[l], Hp, SBp, Hp, M, Hp, Hp, false);
+          }
         } } else if constexpr (BK::dgm_on()) {
           // fused path (hidden size 128): grad[U | b] is formed where the pre-activation cotangents are
           // produced (input_map_adj), so the weight-gradient passes carry no A^T E work
@@ -327,8 +353,11 @@ struct Pipeline {
               bk.ew(f, R * Hp);
             })
           }
-          // s bar += [abar_Z | abar_G | abar_R] [W_z; W_g; W_r]
+          // s bar += [abar_Z | abar_G | abar_R] [W_z; W_g; W_r]  (grouping backends: same stage as the weight gradient
+          // below -- it reads AB and S[l], this writes SBp)
+          bk.nosync(true);
           bk.gemm_nn(AB, 4 * Hp, c.Wp + c.pl.wb[l], Hp, c.Wp + c.pl.wf[l], 3 * Hp, SBp, Hp, M, Hp, 3 * Hp, true);
+          bk.nosync(false);
           // weight gradient of the Z, G, R gates; off the fused path grad[U | b] = Abar^T E rides along
           bk.gemm_tn_acc(AB, 4 * Hp, pb.S[l], Hp, Gp + c.pl.g_w[l], 3 * Hp, Hp, M, Ew, gub, 4 * Hp, c.part, c.part_n);
         }

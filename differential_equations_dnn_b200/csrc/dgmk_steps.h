@@ -30,8 +30,7 @@ DGMK_HD_PLAIN bool heat_chunk(PIPE& P, Carver& cv, size_t mark, const HeatArgs& 
     P.forward(pb);
     HeatInteriorFn f; f.U = pb.U; f.UB = pb.UB; f.Lp = c.Lp; f.kappa = a.kappa; f.inv = a.inv;
     bk.ew(f, r);
-    P.add_loss(r);
-    P.reverse(pb, rb);
+    P.reverse(pb, rb, r);
   }
   {  // companions: IC row (x,0), BC rows (0,t) and (pi,t)  (heat.py:89-94)
     cv.off = mark;
@@ -45,8 +44,7 @@ DGMK_HD_PLAIN bool heat_chunk(PIPE& P, Carver& cv, size_t mark, const HeatArgs& 
     f.tgt[0] = nullptr; f.tgt[1] = a.t_bd1 + p0; f.tgt[2] = a.t_bd2 + p0;
     f.mode[0] = 1; f.mode[1] = 0; f.mode[2] = 0; f.o = 1; f.inv = a.inv;
     bk.ew(f, 3 * r);
-    P.add_loss(3 * r);
-    P.reverse(pb, rb);
+    P.reverse(pb, rb, 3 * r);
   }
   return true;
 }
@@ -74,8 +72,7 @@ DGMK_HD_PLAIN bool ode_like_chunk(PIPE& P, Carver& cv, size_t mark, const OdeArg
       OdeInteriorFn f; f.U = pb.U; f.UB = pb.UB; f.Lp = c.Lp; f.inv = a.inv;
       bk.ew(f, r);
     }
-    P.add_loss(r);
-    P.reverse(pb, rb);
+    P.reverse(pb, rb, r);
   }
   {  // initial-condition rows (simple_ode.py:62; fitzhugh_nagumo.py:95 -- mean over 2B elements)
     cv.off = mark;
@@ -88,8 +85,7 @@ DGMK_HD_PLAIN bool ode_like_chunk(PIPE& P, Carver& cv, size_t mark, const OdeArg
     f.tgt[0] = a.y_ic + p0 * c.n.o; f.tgt[1] = f.tgt[2] = nullptr; f.mode[0] = f.mode[1] = f.mode[2] = 0;
     f.o = c.n.o; f.inv = a.fhn ? a.inv * 0.5f : a.inv;
     bk.ew(f, r);
-    P.add_loss(r);
-    P.reverse(pb, rb);
+    P.reverse(pb, rb, r);
   }
   return true;
 }

@@ -50,7 +50,7 @@ __device__ __forceinline__ T* shp(T* p) {
 // tiles on packed FFMA2, the tile index walks N fastest (a warp shares its A rows by broadcast).
 template <int TM, bool BSH>
 __device__ __noinline__ void gemm_nn_impl(const float* __restrict__ A_, int lda, const float* __restrict__ B_, int ldb, float* __restrict__ C_,
-                                          int ldc, int M, int N, int K, bool acc) {
+                                          int ldc, int M, int N, int K, bool acc, bool sync) {
   const float* A = shp(A_);
   float* C = shp(C_);
   const float* B = BSH ? shp(B_) : B_;
@@ -97,7 +97,7 @@ __device__ __noinline__ void gemm_nn_impl(const float* __restrict__ A_, int lda,
       }
     }
   }
-  __syncthreads();
+  if (sync) __syncthreads();
 }
 
 // column sums with up to four weights per row:
@@ -105,16 +105,28 @@ __device__ __noinline__ void gemm_nn_impl(const float* __restrict__ A_, int lda,
 // thread = (column n, row group g of G = NT / N).  Narrow matrices (N = 1, 4, ...: loss sums, grad b_out) have many
 // groups inside one warp: those are combined by shuffles first, so that the second stage adds at most NT / 32 partials
 // per output (summing 256 partials in one thread cost more than the sums themselves).  Fixed order throughout.
-__device__ __noinline__ void wcolsum_impl(const float* __restrict__ Mat_, int ldm, int N, const float* __restrict__ Wt_, int M, float* out,
-                                          int ldo, float* scratch_) {
-  const float* Mat = shp(Mat_);
-  const float* Wt = Wt_ ? shp(Wt_) : nullptr;
-  float* scratch = shp(scratch_);
-  const int NE = Wt ? 4 : 1;
+struct ColsumJob {
+  const float* Mat; int ldm, N; const float* Wt; int M; float* out; int ldo;
+  int G, Gs, NE; float* scratch;   // filled in by colsum_plan
+};
+// groups of a job and the scratch floats its partials need (cap: what is left of the scratch)
+__device__ __forceinline__ int colsum_plan(ColsumJob& j, float* scratch, int cap) {
+  j.NE = j.Wt ? 4 : 1;
+  const bool narrow = j.N < 32 && (32 % j.N) == 0;
+  j.G = NT / j.N;
+  if (!narrow && j.G * j.NE * j.N > cap) j.G = cap / (j.NE * j.N);
+  j.Gs = narrow ? NT / 32 : j.G;
+  j.scratch = scratch;
+  return j.Gs * j.NE * j.N;
+}
+// first half: every thread's running sums -> one partial per (output, group) in the job's scratch
+__device__ __forceinline__ void colsum_partial(const ColsumJob& j) {
+  const float* Mat = shp(j.Mat);
+  const float* Wt = j.Wt ? shp(j.Wt) : nullptr;
+  float* scratch = shp(j.scratch);
+  const int N = j.N, NE = j.NE, G = j.G, M = j.M, ldm = j.ldm;
   const int tid = threadIdx.x;
   const bool narrow = N < 32 && (32 % N) == 0;
-  int G = NT / N;
-  if (!narrow && G * NE * N > SCRATCH_FLOATS) G = SCRATCH_FLOATS / (NE * N);
   const int n = tid % N, g = tid / N;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   if (g < G) {
@@ -130,7 +142,6 @@ __device__ __noinline__ void wcolsum_impl(const float* __restrict__ Mat_, int ld
       for (int r = g; r < M; r += G) a0 += Mat[r * ldm + n];
     }
   }
-  int Gs = G;   // partials per output that reach the scratch
   if (narrow) {   // the 32 / N groups of a warp -> one partial per warp (whole warps: NT is a multiple of 32)
     for (int off = N; off < 32; off <<= 1) {
       a0 += __shfl_xor_sync(0xffffffffu, a0, off);
@@ -140,7 +151,6 @@ __device__ __noinline__ void wcolsum_impl(const float* __restrict__ Mat_, int ld
         a3 += __shfl_xor_sync(0xffffffffu, a3, off);
       }
     }
-    Gs = NT / 32;
     if ((tid & 31) < N) {
       float* s = scratch + ((tid >> 5) * NE) * N + n;
       s[0] = a0;
@@ -151,23 +161,66 @@ __device__ __noinline__ void wcolsum_impl(const float* __restrict__ Mat_, int ld
     s[0] = a0;
     if (Wt) { s[N] = a1; s[2 * N] = a2; s[3 * N] = a3; }
   }
-  __syncthreads();
-  for (int i = tid; i < NE * N; i += NT) {
+}
+// second half (after a barrier): the partials of an output in group order, added to the accumulator
+__device__ __forceinline__ void colsum_finish(const ColsumJob& j, int tid0) {
+  const float* scratch = shp(j.scratch);
+  const int N = j.N, NEN = j.NE * j.N;
+  for (int i = (int)threadIdx.x - tid0; i >= 0 && i < NEN; i += NT) {
     float t = 0.f;
-    for (int q = 0; q < Gs; ++q) t += scratch[q * NE * N + i];
+    for (int q = 0; q < j.Gs; ++q) t += scratch[q * NEN + i];
     const int e = i / N, c = i - e * N;
-    out[(ldo > 0 ? e * ldo : e * N) + c] += t;
+    j.out[(j.ldo > 0 ? e * j.ldo : e * N) + c] += t;
   }
+}
+__device__ __noinline__ void wcolsum_impl(const float* __restrict__ Mat_, int ldm, int N, const float* __restrict__ Wt_, int M, float* out,
+                                          int ldo, float* scratch_) {
+  ColsumJob j; j.Mat = Mat_; j.ldm = ldm; j.N = N; j.Wt = Wt_; j.M = M; j.out = out; j.ldo = ldo;
+  colsum_plan(j, scratch_, SCRATCH_FLOATS);
+  colsum_partial(j);
+  __syncthreads();
+  colsum_finish(j, 0);
+  __syncthreads();
+}
+// The three column sums at the head of a reverse pass in ONE stage (two barriers instead of six): the pass's loss rows
+// (Lp == nullptr: none), grad W_out = UB^T S_L and grad b_out = UB^T E.  Same arithmetic and summation order as three
+// wcolsum_impl calls; the second halves run on different warps (tid0 = 0 / 32 / 128 when the CTA has that many threads).
+__device__ __noinline__ void wcolsum3_impl(const float* Lp, int loss_rows, float* loss_out, const float* SL, int Hp, const float* UB, int M,
+                                           float* gw_out, const float* E, float* gb_out, float* scratch_) {
+  ColsumJob jl, jw, jb;
+  jl.Mat = Lp; jl.ldm = 1; jl.N = 1; jl.Wt = nullptr; jl.M = loss_rows; jl.out = loss_out; jl.ldo = 0;
+  jw.Mat = SL; jw.ldm = Hp; jw.N = Hp; jw.Wt = UB; jw.M = M; jw.out = gw_out; jw.ldo = 0;
+  jb.Mat = UB; jb.ldm = 4; jb.N = 4; jb.Wt = E; jb.M = M; jb.out = gb_out; jb.ldo = 0;
+  int used = 0;
+  if (Lp) used += colsum_plan(jl, scratch_, SCRATCH_FLOATS);
+  used += colsum_plan(jb, scratch_ + used, SCRATCH_FLOATS - used);
+  colsum_plan(jw, scratch_ + used, SCRATCH_FLOATS - used);
+  if (Lp) colsum_partial(jl);
+  colsum_partial(jb);
+  colsum_partial(jw);
+  __syncthreads();
+  colsum_finish(jw, 0);                                  // 4 * Hp outputs: threads 0 .. 4 Hp - 1
+  colsum_finish(jb, NT >= 256 ? NT - 32 : 0);            // 16 outputs
+  if (Lp) colsum_finish(jl, NT >= 256 ? NT - 64 : 0);    // 1 output
   __syncthreads();
 }
 
 // out[N, Kd] += A^T S over the tile's M rows.  4 x 4 register tiles over (n, kd); when there are fewer tiles than
 // threads the rows are split over thread groups that are combined through the scratch in group order.
+// E != nullptr: outE[e * ldoE + n] += sum_m A[m, n] E[m, e] (grad[U | b] = Abar^T E) in the SAME stage -- its running
+// sums go to the second scratch before the tiles start, its second half runs after the tiles' barrier.
 __device__ __noinline__ void gemm_tn_impl(const float* __restrict__ A_, int lda, const float* __restrict__ S_, int lds, float* out, int N, int Kd,
-                                          int M, float* scratch_) {
+                                          int M, float* scratch_, const float* E, float* outE, int ldoE) {
   const float* A = shp(A_);
   const float* S = shp(S_);
   float* scratch = shp(scratch_);
+  ColsumJob je;
+  if (SCRATCH2_FLOATS == 0) E = nullptr;   // (the caller runs the column sums as a stage of their own)
+  if (E) {
+    je.Mat = A_; je.ldm = lda; je.N = N; je.Wt = E; je.M = M; je.out = outE; je.ldo = ldoE;
+    colsum_plan(je, scratch_ + SCRATCH_FLOATS, SCRATCH2_FLOATS);
+    colsum_partial(je);
+  }
   const int nkg = Kd >> 2, ntiles = (N >> 2) * nkg;
   int G = NT / ntiles;
   if (G < 1) G = 1;
@@ -220,6 +273,10 @@ __device__ __noinline__ void gemm_tn_impl(const float* __restrict__ A_, int lda,
     }
     if (G > 1) __syncthreads();   // (G > 1 implies a single pass of the t0 loop)
   }
+  if (E) {
+    if (G == 1) __syncthreads();   // the column-sum partials are visible (G > 1: the barriers above did that)
+    colsum_finish(je, 0);
+  }
   __syncthreads();
 }
 
@@ -264,8 +321,12 @@ struct TileBackend {
   static constexpr bool act_on(int id) { return (ACTMASK >> id) & 1; }
   static constexpr bool mlp_on() { return MLP; }
   static constexpr bool dgm_on() { return DGM; }
-  float* scratch;   // SCRATCH_FLOATS floats of shared memory
+  float* scratch;   // SCRATCH_TOTAL_FLOATS floats of shared memory (main scratch, then the A^T E scratch)
   int64_t hl_stride;
+  // stage grouping (BackendTraitsAll::nosync): inside a group the element-wise / gemm_nn stages skip their barrier
+  static constexpr bool kGroupsStages = true;
+  bool grouped;
+  __device__ __forceinline__ void nosync(bool on) { grouped = on; }
   bool w_shared, g_shared;   // packed weights / gradient accumulators live in shared memory (else L2)
   // stage timeline of CTA 0 (dgmk_tile_profile): (clock64, stage kind) after every stage; nullptr = off
   long long* prof; int prof_i, prof_n;
@@ -308,6 +369,7 @@ struct TileBackend {
   template <class F>
   __device__ __forceinline__ void ew(const F& f, int64_t n) {
     for (int i = threadIdx.x; i < (int)n; i += NT) f((int64_t)i);
+    if (grouped) return;
     __syncthreads();
     stamp(1);
   }
@@ -315,6 +377,7 @@ struct TileBackend {
   __device__ __forceinline__ void ew4(const F& f, int64_t n) {
     const int n4 = (int)(n >> 2);
     for (int k = threadIdx.x; k < n4; k += NT) f.vec4((int64_t)k);
+    if (grouped) return;
     __syncthreads();
     stamp(2);
   }
@@ -323,26 +386,32 @@ struct TileBackend {
                                           int64_t M_, int N, int K, bool acc) {
     const int M = (int)M_;
     const bool big = ((M + 3) >> 2) * (N >> 2) > NT;
+    const bool sync = !grouped;
     if (w_shared) {
-      if (big) gemm_nn_impl<8, true>(A, (int)lda, B, (int)ldb, C, (int)ldc, M, N, K, acc);
-      else gemm_nn_impl<4, true>(A, (int)lda, B, (int)ldb, C, (int)ldc, M, N, K, acc);
+      if (big) gemm_nn_impl<8, true>(A, (int)lda, B, (int)ldb, C, (int)ldc, M, N, K, acc, sync);
+      else gemm_nn_impl<4, true>(A, (int)lda, B, (int)ldb, C, (int)ldc, M, N, K, acc, sync);
     } else {
-      if (big) gemm_nn_impl<8, false>(A, (int)lda, B, (int)ldb, C, (int)ldc, M, N, K, acc);
-      else gemm_nn_impl<4, false>(A, (int)lda, B, (int)ldb, C, (int)ldc, M, N, K, acc);
+      if (big) gemm_nn_impl<8, false>(A, (int)lda, B, (int)ldb, C, (int)ldc, M, N, K, acc, sync);
+      else gemm_nn_impl<4, false>(A, (int)lda, B, (int)ldb, C, (int)ldc, M, N, K, acc, sync);
     }
-    stamp(3);
+    if (sync) stamp(3);
   }
   __device__ __forceinline__ void wcolsum_acc(const float* Mat, int64_t ldm, int N, const float* Wt, int64_t M, float* out, float*, int64_t,
                                               int64_t ldo = 0) {
     wcolsum_impl(Mat, (int)ldm, N, Wt, (int)M, out, (int)ldo, scratch);
     stamp(4);
   }
+  __device__ __forceinline__ void wcolsum3(const float* Lp, int64_t loss_rows, float* loss_out, const float* SL, int Hp, const float* UB,
+                                           int64_t M, float* gw_out, const float* E, float* gb_out) {
+    wcolsum3_impl(Lp, (int)loss_rows, loss_out, SL, Hp, UB, (int)M, gw_out, E, gb_out, scratch);
+    stamp(4);
+  }
   // (+ outE[e * ldoE + n] += sum_m A[m, n] E[m, e]: grad[U | b] = Abar^T E)
   __device__ __forceinline__ void gemm_tn_acc(const float* A, int64_t lda, const float* S, int64_t lds, float* out, int N, int Kd, int64_t M,
                                               const float* E, float* outE, int64_t ldoE, float*, int64_t) {
-    gemm_tn_impl(A, (int)lda, S, (int)lds, out, N, Kd, (int)M, scratch);
+    gemm_tn_impl(A, (int)lda, S, (int)lds, out, N, Kd, (int)M, scratch, E, outE, (int)ldoE);
     stamp(5);
-    if (E) { wcolsum_impl(A, (int)lda, N, E, (int)M, outE, (int)ldoE, scratch); stamp(6); }
+    if (E && SCRATCH2_FLOATS == 0) { wcolsum_impl(A, (int)lda, N, E, (int)M, outE, (int)ldoE, scratch); stamp(6); }
   }
   __device__ __forceinline__ void rowdot(const float* S, int64_t lds, const float* W, const float* b, float* U, int64_t M, int Hp, int o, int C) {
     if (w_shared) rowdot_impl<true>(S, (int)lds, W, b, U, (int)M, Hp, o, C);
@@ -364,8 +433,9 @@ template <int PROB, class BK>
 __global__ void __launch_bounds__(NT, PROB == PROB_HEAT ? 1 : 2) tile_step_kernel(const __grid_constant__ TileParams prm) {
   float* sp = g_tile_smem;
   BK bk;
-  bk.scratch = sp; sp += SCRATCH_FLOATS;
+  bk.scratch = sp; sp += SCRATCH_TOTAL_FLOATS;
   bk.hl_stride = 0;
+  bk.grouped = false;
   bk.w_shared = prm.w_smem != 0; bk.g_shared = prm.g_smem != 0;
   bk.prof = blockIdx.x == 0 ? prm.prof : nullptr; bk.prof_i = 0; bk.prof_n = prm.prof_n;
   bk.stamp(0);

@@ -10,6 +10,13 @@ namespace tk {
 constexpr int NT = 256;                 // threads per CTA, one CTA per SM (measured: 512 threads 19.3 ms, 1024 25.4 ms, 256 16.2 ms
                                         // per 2^20 heat rows at hidden size 32 -- fewer idle lanes at the stage barriers, no spills)
 constexpr int SCRATCH_FLOATS = 2048;    // cross-group reduction scratch (8 KB)
+#ifndef DGMK_TILE_SCRATCH2
+#define DGMK_TILE_SCRATCH2 0
+#endif
+// second scratch: > 0 lets the A^T E column sums share a stage with the weight-gradient tiles (1536 floats cover every
+// shape).  Measured (profiles/r02_notes.md): the stage it saves is worth less than the ~6 % of tile points the 6 KB cost.
+constexpr int SCRATCH2_FLOATS = DGMK_TILE_SCRATCH2;
+constexpr int SCRATCH_TOTAL_FLOATS = SCRATCH_FLOATS + SCRATCH2_FLOATS;
 constexpr int SMEM_MAX = 232448;        // 227 KB opt-in limit per CTA on sm_100
 constexpr int SMEM_HALF = 115712;       // two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2
 constexpr int FLUSH_TILES = 256;        // tiles per FP32 accumulation segment
