@@ -465,6 +465,14 @@ struct CudaBackend : BackendTraitsAll {
       lane_gemm(Yp, Hp, Wb, Hp, M, 1, e, 3.0);
     } else if (!err) err = "internal: fused path called with an unsupported channel set";
   }
+  // MLP reverse, layers below the top one: ABout = act_adj(ABin Wt^T, a-form G of the layer below) in one launch
+  template <class CS, int ACT>
+  void mlp_rev_fused(const float* ABin, const float* Wt, const float* G, float* ABout, int Hp, int64_t M) {
+    if constexpr (CS::C == 1 || CS::C == 2 || CS::C == 4) {
+      lg::MlpRevEpi<CS, ACT> e; e.G = G; e.AB = ABout;
+      lane_gemm(ABin, Hp, Wt, Hp, M, 1, e, 3.0);   // read abar_l, the a-form below; write abar_{l-1}
+    } else if (!err) err = "internal: fused path called with an unsupported channel set";
+  }
   // C[M, Hp] = X[M, Hp] Wt[Hp, Hp]^T on the lane kernel (MLP data gradient)
   void lane_store(const float* X, int64_t ldx, const float* Wt, float* C, int64_t ldc, int Hp, int64_t M) {
     lg::StoreEpi<false> e; e.C = C; e.ldc = ldc;

@@ -220,6 +220,43 @@ struct MlpActEpi {
   }
 };
 
+// MLP reverse: y bar of layer l-1 = abar_l W_l arrives from the GEMM; abar_{l-1} = act_adj(y bar, a-form of layer l-1)
+// (adjoint of neural_networks.py:242-243; stand-alone form: lane_store + MlpRevFn -- the cotangent never visits HBM)
+template <class CS, int ACT>
+struct MlpRevEpi {
+  const float* G; float* AB;
+  static constexpr int C = CS::C;
+  struct Const { int j; };
+  using Tile = NoTile;
+  struct State {};
+  __device__ __forceinline__ void finish(const State&, const Const&, int) const {}
+  struct Pre { float af[8]; };
+  __device__ __forceinline__ Const init(int, int j) const { Const k; k.j = j; return k; }
+  __device__ __forceinline__ void tile(Tile&, const Const&, int64_t, int64_t, int) const {}
+  template <bool FULL>
+  __device__ __forceinline__ void prefetch(Pre& p, const Tile&, const Const& k, int64_t row0, int, int64_t M) const {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) p.af[q] = ldg_f(G + clampr<FULL>(row0 + q, M) * HP + k.j);
+  }
+  template <bool FULL>
+  __device__ __forceinline__ void apply(const Pre& p, State&, const Tile&, int, const Const& k, int64_t row0, int64_t M, const float (&acc)[8]) const {
+    float abo[8];
+#pragma unroll
+    for (int pp = 0; pp < 8 / C; ++pp) {
+      float af[C], yb[C], ab[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) { af[c] = p.af[pp * C + c]; yb[c] = acc[pp * C + c]; }
+      act_adj<CS, ACT>(yb, af, ab);
+#pragma unroll
+      for (int c = 0; c < C; ++c) abo[pp * C + c] = ab[c];
+    }
+    float* o = AB + row0 * HP + k.j;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (FULL || row0 + q < M) o[q * HP] = abo[q];
+  }
+};
+
 // (s*R)bar = abar_H W_h arrives from the GEMM; abar_R = act_adj((sR)bar * s), s bar += (sR)bar * R
 // (adjoint of dgm_net.py:65-66; stand-alone form: DgmRev2Fn)
 template <class CS, int ACT>

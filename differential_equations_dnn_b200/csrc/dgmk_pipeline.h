@@ -303,14 +303,26 @@ struct Pipeline {
       bk.ew4(fo, M * Hp);
     }
     DGMK_CS_SWITCH(pb.cs, CS, {
+      float* fcur = nullptr; float* fnxt = nullptr;   // fused MLP reverse: abar_l ping-pong
       for (int l = n.L - 1; l >= 0; --l) {
         float* AB = ip ? pb.G[l] : rb.AB;      // pre-activation cotangents
         if (!n.is_dgm()) { if constexpr (BK::mlp_on()) {
-          DGMK_ACT_SWITCH(n.act, ACT, {
-            MlpRevFn<CS, ACT> f; f.G = pb.G[l]; f.YB = SBn; f.AB = AB; f.Hp = Hp;
-            bk.note_bytes(3 * unit);
-            bk.ew(f, R * Hp);
-          })
+          // Fused path (hidden size 128): below the top layer the data gradient and the activation adjoint of the
+          // layer underneath are ONE launch (MlpRevEpi) -- abar_l ping-pongs between rb.AB and rb.SBb and the
+          // cotangent y bar never visits HBM; only the bottom layer's data gradient is stored (into SBn, which the
+          // top layer's adjoint has already consumed) for the input layer.
+          const bool fz = !ip && n.L > 1 && bk.lane_ok(Hp, pb.cs);
+          if (fz) {
+            if (l == n.L - 1) { fcur = rb.AB; fnxt = rb.SBb; }
+            AB = fcur;
+          }
+          if (!fz || l == n.L - 1) {
+            DGMK_ACT_SWITCH(n.act, ACT, {
+              MlpRevFn<CS, ACT> f; f.G = pb.G[l]; f.YB = SBn; f.AB = AB; f.Hp = Hp;
+              bk.note_bytes(3 * unit);
+              bk.ew(f, R * Hp);
+            })
+          }
           if constexpr (BK::kGroupsStages) {   // the data gradient (AB -> SBp) and the weight gradient (AB, S[l] -> Gp): one stage
             bk.nosync(true);
             bk.gemm_nn(AB, Hp, c.Wp + c.pl.wb[l], Hp, c.Wp + c.pl.wf[l], Hp, SBp, Hp, M, Hp, Hp, false);
@@ -319,6 +331,17 @@ struct Pipeline {
           } else {
           // grad W = Abar^T Y_prev, and grad b (row 2 of Abar^T E) in the same pass
           bk.gemm_tn_acc(AB, Hp, pb.S[l], Hp, Gp + c.pl.g_w[l], Hp, Hp, M, pb.E, Gp + c.pl.g_ub[l], Hp, c.part, c.part_n);
+          if (fz) {
+            if (l > 0) {
+              DGMK_ACT_SWITCH(n.act, ACT, {
+                bk.template mlp_rev_fused<CS, ACT>(AB, c.Wp + c.pl.wf[l], pb.G[l - 1], fnxt, Hp, M);
+              })
+              float* t2 = fcur; fcur = fnxt; fnxt = t2;
+            } else {
+              bk.lane_store(AB, Hp, c.Wp + c.pl.wf[l], SBn, Hp, Hp, M);
+            }
+            continue;   // (no ping-pong of the state cotangents on this path: SBn stays the buffer the input layer reads)
+          }
           if (bk.lane_ok(Hp, CS_V)) bk.lane_store(AB, Hp, c.Wp + c.pl.wf[l], SBp, Hp, Hp, M);
           else bk.gemm_nn(AB, Hp, c.Wp + c.pl.wb[l], Hp, c.Wp + c.pl.wf[l], Hp, SBp, Hp, M, Hp, Hp, false);
           }
