@@ -473,6 +473,14 @@ struct CudaBackend : BackendTraitsAll {
       lane_gemm(ABin, Hp, Wt, Hp, M, 1, e, 3.0);   // read abar_l, the a-form below; write abar_{l-1}
     } else if (!err) err = "internal: fused path called with an unsupported channel set";
   }
+  // MLP reverse, bottom layer: ABout = act_adj(ABin Wt^T, input-layer a-form) in one launch (lane_store + InputRevFn)
+  template <class CS, int ACT>
+  void input_rev_fused(const float* ABin, const float* Wt, const F4* inb, const float* S0, float* ABout, int Hp, int64_t M) {
+    if constexpr (CS::C == 1 || CS::C == 2 || CS::C == 4) {
+      lg::InputRevEpi<CS, ACT> e; e.inb = inb; e.S0 = S0; e.AB = ABout;
+      lane_gemm(ABin, Hp, Wt, Hp, M, 1, e, 2.0 + 1.0 / CS::C);   // read abar_0, the value rows of s0; write abar_in
+    } else if (!err) err = "internal: fused path called with an unsupported channel set";
+  }
   // C[M, Hp] = X[M, Hp] Wt[Hp, Hp]^T on the lane kernel (MLP data gradient)
   void lane_store(const float* X, int64_t ldx, const float* Wt, float* C, int64_t ldc, int Hp, int64_t M) {
     lg::StoreEpi<false> e; e.C = C; e.ldc = ldc;

@@ -257,6 +257,48 @@ struct MlpRevEpi {
   }
 };
 
+// MLP reverse, bottom layer: y bar of the INPUT layer = abar_0 W_0 arrives from the GEMM; abar_in = act_adj(y bar, input
+// a-form) with the a-form rebuilt like InputRevFn does (value from S0, tangents = the input weights)
+template <class CS, int ACT>
+struct InputRevEpi {
+  const F4* inb; const float* S0; float* AB;
+  static constexpr int C = CS::C;
+  struct Const { F4 w; int j; };
+  using Tile = NoTile;
+  struct State {};
+  __device__ __forceinline__ void finish(const State&, const Const&, int) const {}
+  struct Pre { float s0[8 / C]; };
+  __device__ __forceinline__ Const init(int, int j) const { Const k; k.w = inb[j]; k.j = j; return k; }
+  __device__ __forceinline__ void tile(Tile&, const Const&, int64_t, int64_t, int) const {}
+  template <bool FULL>
+  __device__ __forceinline__ void prefetch(Pre& p, const Tile&, const Const& k, int64_t row0, int, int64_t M) const {
+#pragma unroll
+    for (int pp = 0; pp < 8 / C; ++pp) p.s0[pp] = ldg_f(S0 + clampr<FULL>(row0 + pp * C, M) * HP + k.j);
+  }
+  template <bool FULL>
+  __device__ __forceinline__ void apply(const Pre& p, State&, const Tile&, int, const Const& k, int64_t row0, int64_t M, const float (&acc)[8]) const {
+    float abo[8];
+#pragma unroll
+    for (int pp = 0; pp < 8 / C; ++pp) {
+      float af[C], yb[C], ab[C];
+      af[0] = p.s0[pp];
+#pragma unroll
+      for (int kk = 0; kk < CS::ND; ++kk) af[1 + kk] = (kk == 0) ? k.w.x : k.w.y;
+#pragma unroll
+      for (int qq = 0; qq < CS::NP; ++qq) af[1 + CS::ND + qq] = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) yb[c] = acc[pp * C + c];
+      act_adj<CS, ACT>(yb, af, ab);
+#pragma unroll
+      for (int c = 0; c < C; ++c) abo[pp * C + c] = ab[c];
+    }
+    float* o = AB + row0 * HP + k.j;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (FULL || row0 + q < M) o[q * HP] = abo[q];
+  }
+};
+
 // (s*R)bar = abar_H W_h arrives from the GEMM; abar_R = act_adj((sR)bar * s), s bar += (sR)bar * R
 // (adjoint of dgm_net.py:65-66; stand-alone form: DgmRev2Fn)
 template <class CS, int ACT>

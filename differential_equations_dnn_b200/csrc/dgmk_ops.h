@@ -466,6 +466,29 @@ struct OutRevFn {
   }
 };
 
+// OutRevFn followed by MlpRevFn of the top hidden layer in one pass: the output-layer cotangent y bar = UB outw is
+// formed in registers (same sums as OutRevFn) instead of being written and re-read
+template <class CS, int ACT>
+struct OutMlpRevFn {
+  const float* UB; const float* outw; const float* G; float* AB; int Hp; int o;
+  DGMK_HD void operator()(int64_t i) const {
+    DGMK_SMEM(UB); DGMK_SMEM(G); DGMK_SMEM(AB);
+    int64_t p = idiv(i, Hp); int j = (int)(i - p * Hp);
+    float af[CS::C], yb[CS::C], ab[CS::C];
+    int64_t base = (p * CS::C) * Hp + j;
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) {
+      af[c] = G[base + (int64_t)c * Hp];
+      float v = 0.f;
+      for (int m = 0; m < o; ++m) v += UB[(p * CS::C + c) * 4 + m] * outw[m * Hp + j];
+      yb[c] = v;
+    }
+    act_adj<CS, ACT>(yb, af, ab);
+#pragma unroll
+    for (int c = 0; c < CS::C; ++c) AB[base + (int64_t)c * Hp] = ab[c];
+  }
+};
+
 // ================================ losses =========================================
 // U / UB are [rows*C][4]: output jets (column m = output component) and their
 // cotangent seeds.  Lp[p] is the point's (already scaled) loss contribution.

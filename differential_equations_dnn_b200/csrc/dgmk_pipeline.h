@@ -287,6 +287,8 @@ struct Pipeline {
     float* SBn = rb.SBa;  // cotangent of the current layer's output
     float* SBp = rb.SBb;  // (in-place mode: the same buffer -- every stage reads an element before it overwrites it)
     OutRevFn fo; fo.UB = pb.UB; fo.outw = c.Wp + c.pl.outw; fo.SB = SBn; fo.Hp = Hp; fo.o = n.o;
+    // fused MLP reverse (hidden size 128, see the layer loop): the output-layer adjoint is part of the top layer's stage
+    const bool fz = !ip && !n.is_dgm() && bk.lane_ok(Hp, pb.cs);
     if constexpr (BK::kGroupsStages) {
       bk.nosync(true);     // SBn is a buffer of its own: nothing the column sums read or write
       bk.ew4(fo, M * Hp);
@@ -299,24 +301,32 @@ struct Pipeline {
       // output layer: grad W_out = UB^T S_L, grad b_out = sum of value-row cotangents
       bk.wcolsum_acc(pb.S[n.L], Hp, Hp, pb.UB, M, Gp + c.pl.g_outw, c.part, c.part_n);
       bk.wcolsum_acc(pb.UB, 4, 4, pb.E, M, Gp + c.pl.g_outb, c.part, c.part_n);
-      bk.note_bytes(unit + 16.0 * M);
-      bk.ew4(fo, M * Hp);
+      if (!fz) {
+        bk.note_bytes(unit + 16.0 * M);
+        bk.ew4(fo, M * Hp);
+      }
     }
+    float* ABin_fused = nullptr;
     DGMK_CS_SWITCH(pb.cs, CS, {
       float* fcur = nullptr; float* fnxt = nullptr;   // fused MLP reverse: abar_l ping-pong
       for (int l = n.L - 1; l >= 0; --l) {
         float* AB = ip ? pb.G[l] : rb.AB;      // pre-activation cotangents
         if (!n.is_dgm()) { if constexpr (BK::mlp_on()) {
-          // Fused path (hidden size 128): below the top layer the data gradient and the activation adjoint of the
-          // layer underneath are ONE launch (MlpRevEpi) -- abar_l ping-pongs between rb.AB and rb.SBb and the
-          // cotangent y bar never visits HBM; only the bottom layer's data gradient is stored (into SBn, which the
-          // top layer's adjoint has already consumed) for the input layer.
-          const bool fz = !ip && n.L > 1 && bk.lane_ok(Hp, pb.cs);
+          // Fused path (hidden size 128): the top layer's activation adjoint forms the output-layer cotangent in
+          // registers (OutMlpRevFn); below it the data gradient and the activation adjoint of the layer underneath
+          // are ONE launch (MlpRevEpi; at the bottom InputRevEpi for the input layer) -- abar_l ping-pongs between
+          // rb.AB and rb.SBb and no cotangent y bar ever visits HBM.
           if (fz) {
             if (l == n.L - 1) { fcur = rb.AB; fnxt = rb.SBb; }
             AB = fcur;
           }
-          if (!fz || l == n.L - 1) {
+          if (fz && l == n.L - 1) {
+            DGMK_ACT_SWITCH(n.act, ACT, {
+              OutMlpRevFn<CS, ACT> f; f.UB = pb.UB; f.outw = c.Wp + c.pl.outw; f.G = pb.G[l]; f.AB = AB; f.Hp = Hp; f.o = n.o;
+              bk.note_bytes(2 * unit + 16.0 * M);
+              bk.ew(f, R * Hp);
+            })
+          } else if (!fz) {
             DGMK_ACT_SWITCH(n.act, ACT, {
               MlpRevFn<CS, ACT> f; f.G = pb.G[l]; f.YB = SBn; f.AB = AB; f.Hp = Hp;
               bk.note_bytes(3 * unit);
@@ -338,9 +348,12 @@ struct Pipeline {
               })
               float* t2 = fcur; fcur = fnxt; fnxt = t2;
             } else {
-              bk.lane_store(AB, Hp, c.Wp + c.pl.wf[l], SBn, Hp, Hp, M);
+              DGMK_ACT_SWITCH(n.in_act(), ACT, {
+                bk.template input_rev_fused<CS, ACT>(AB, c.Wp + c.pl.wf[l], inb(), pb.S[0], fnxt, Hp, M);
+              })
+              ABin_fused = fnxt;
             }
-            continue;   // (no ping-pong of the state cotangents on this path: SBn stays the buffer the input layer reads)
+            continue;   // (no state cotangents on this path)
           }
           if (bk.lane_ok(Hp, CS_V)) bk.lane_store(AB, Hp, c.Wp + c.pl.wf[l], SBp, Hp, Hp, M);
           else bk.gemm_nn(AB, Hp, c.Wp + c.pl.wb[l], Hp, c.Wp + c.pl.wf[l], Hp, SBp, Hp, M, Hp, Hp, false);
@@ -386,6 +399,9 @@ struct Pipeline {
         }
         float* t = SBn; SBn = SBp; SBp = t;
       }
+      if (ABin_fused) {
+        bk.wcolsum_acc(ABin_fused, Hp, Hp, pb.E, M, Gp + c.pl.g_inb, c.part, c.part_n);
+      } else {
       DGMK_ACT_SWITCH(n.in_act(), ACT, {
         float* ABin = ip ? SBn : rb.AB;
         InputRevFn<CS, ACT> f; f.inb = inb(); f.S0 = pb.S[0]; f.SB = SBn; f.AB = ABin; f.Hp = Hp; f.ldab = Hp;
@@ -393,6 +409,7 @@ struct Pipeline {
         bk.ew4(f, R * Hp);
         bk.wcolsum_acc(ABin, Hp, Hp, pb.E, M, Gp + c.pl.g_inb, c.part, c.part_n);
       })
+      }
     })
   }
 

@@ -367,6 +367,8 @@ struct TileBackend {
   __device__ void lane_store(const float*, int64_t, const float*, float*, int64_t, int, int64_t) {}
   template <class CS, int ACT>
   __device__ void mlp_rev_fused(const float*, const float*, const float*, float*, int, int64_t) {}
+  template <class CS, int ACT>
+  __device__ void input_rev_fused(const float*, const float*, const dgmk::F4*, const float*, float*, int, int64_t) {}
 
   template <class F>
   __device__ __forceinline__ void ew(const F& f, int64_t n) {

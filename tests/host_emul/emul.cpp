@@ -36,6 +36,8 @@ struct HostBackend : dgmk::BackendTraitsAll {
   void lane_store(const float*, int64_t, const float*, float*, int64_t, int, int64_t) {}
   template <class CS, int ACT>
   void mlp_rev_fused(const float*, const float*, const float*, float*, int, int64_t) {}
+  template <class CS, int ACT>
+  void input_rev_fused(const float*, const float*, const dgmk::F4*, const float*, float*, int, int64_t) {}
   void gemm_nn(const float* A, int64_t lda, const float* B, int64_t ldb, const float* Bt, int64_t ldbt, float* C, int64_t ldc, int64_t M,
                int N, int K, bool acc) {
     // both packed orientations must describe the same matrix (checks the packing tables)
