@@ -406,9 +406,9 @@ def main():
     import types
     import torch.distributed as dist
     from differential_equations_dnn_b200 import (_cabi, dgm_net, neural_networks, heat, simple_ode, fitzhugh_nagumo,
-                                                 fredholm, optim, parallel)
+                                                 fredholm, optim, parallel, _loop)
     pk = types.SimpleNamespace(dgm_net=dgm_net, neural_networks=neural_networks, heat=heat, simple_ode=simple_ode,
-                               fitzhugh_nagumo=fitzhugh_nagumo, fredholm=fredholm)
+                               fitzhugh_nagumo=fitzhugh_nagumo, fredholm=fredholm, _loop=_loop)
 
     lib = _cabi.load()  # raises if the CUDA library is missing: no fallback
     assert torch.cuda.is_available(), "bench.py (b200 arm) needs a GPU"
@@ -552,20 +552,21 @@ def driver_latency(pk, wl, dev):
     import io
     rows = {"heat": 64, "ode": 64, "fhn": 100, "fredholm": 32}[wl.name]
 
-    def run(n, graph):
+    def run(n, graph, philox=False):
+        smp = {"sampler": "philox"} if philox else {}
         net = wl.build_net(pk).to(dev)
         with contextlib.redirect_stdout(io.StringIO()):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             if wl.name == "heat":
-                pk.heat.minimize_loss_dgm(net, iterations=n, batch_size=rows, lrate=1e-4, cuda_graph=graph)
+                pk.heat.minimize_loss_dgm(net, iterations=n, batch_size=rows, lrate=1e-4, cuda_graph=graph, **smp)
             elif wl.name == "ode":
-                pk.simple_ode.minimize_loss_dgm(net, y_ic=2.0, iterations=n, batch_size=rows, lrate=1e-4, cuda_graph=graph)
+                pk.simple_ode.minimize_loss_dgm(net, y_ic=2.0, iterations=n, batch_size=rows, lrate=1e-4, cuda_graph=graph, **smp)
             elif wl.name == "fhn":
                 pk.fitzhugh_nagumo.minimize_loss_dgm(net, torch.zeros([rows, 2], device=dev), iterations=n, batch_size=rows,
-                                                     lrate=1e-4, sampler="grid", cuda_graph=graph)
+                                                     lrate=1e-4, sampler="philox" if philox else "grid", cuda_graph=graph)
             else:
-                pk.fredholm.minimize_loss_dgm(net, iterations=n, batch_size=rows, lrate=1e-4, k=50, cuda_graph=graph)
+                pk.fredholm.minimize_loss_dgm(net, iterations=n, batch_size=rows, lrate=1e-4, k=50, cuda_graph=graph, **smp)
             torch.cuda.synchronize()
         return time.perf_counter() - t0
     try:
@@ -574,8 +575,12 @@ def driver_latency(pk, wl, dev):
         run(1011, True)                 # CUDA events around the 1000 replays (_loop.last_timing): capture excluded
         lt = pk._loop.last_timing
         graph = lt["ms"] * 1e-3 / max(lt["replays"], 1)
+        run(30, True, True)
+        run(1011, True, True)           # the same with the on-device Philox sampler (one sampler launch per iteration)
+        lt = pk._loop.last_timing
+        graph_philox = lt["ms"] * 1e-3 / max(lt["replays"], 1)
         return {"rows": rows, "k": 50 if wl.name == "fredholm" else None, "eager_us_per_iteration": eager * 1e6,
-                "cuda_graph_us_per_iteration": graph * 1e6,
+                "cuda_graph_us_per_iteration": graph * 1e6, "cuda_graph_philox_us_per_iteration": graph_philox * 1e6,
                 "what": "this package's minimize_loss_dgm at the reference driver's shipped batch size (sampler + fused step + "
                         "fused Adam + loss record per iteration); eager: difference of two run lengths, graph: CUDA events around 1000 replays"}
     except Exception as e:

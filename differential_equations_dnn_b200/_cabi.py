@@ -57,6 +57,9 @@ _SIGNATURES = {
                             C.c_int64, _P]),
     "dgmk_adam_dev": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
                                 _P, _P]),
+    "dgmk_sample_uniform": (C.c_int, [_P, C.c_int64, C.c_float, C.c_float, C.c_ulonglong, C.c_uint32, _P, C.c_longlong, _P]),
+    "dgmk_sample_heat": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_ulonglong, _P,
+                                   C.c_longlong, _P]),
 }
 # diagnostics exported only by the CUDA library (bench.py)
 _CUDA_ONLY = {

@@ -12,11 +12,13 @@ import torch
 last_timing = {"replays": 0, "ms": 0.0}
 
 
-def graphed_loop(step, iterations, device, warmup=11):
+def graphed_loop(step, iterations, device, warmup=11, counter=None):
     """step() -> 0-dim loss tensor; it must do its own zero_grad / backward / optimizer.step with
-    device-side state only.  Returns the list of losses (one host read at the end)."""
+    device-side state only.  Returns the list of losses (one host read at the end).
+    counter: a zeroed 1-element int64 device tensor to use as the iteration counter -- the on-device sampler
+    (`sampler.PhiloxSampler.step`) reads it, so every replay draws fresh points with no extra launch."""
     losses = torch.zeros(max(iterations, 1), device=device)
-    idx = torch.zeros(1, dtype=torch.int64, device=device)
+    idx = counter if counter is not None else torch.zeros(1, dtype=torch.int64, device=device)
 
     def one_iteration():
         loss = step()

@@ -341,6 +341,35 @@ struct Api {
     bk.ew(f, P);
     return finish(bk);
   }
+  // ------------------------------------------------------------------ on-device sampler
+  static PhiloxKey philox_key(unsigned long long seed, const long long* step_dev, long long step_add) {
+    PhiloxKey k; k.k0 = (uint32_t)seed; k.k1 = (uint32_t)(seed >> 32); k.step_dev = step_dev; k.step_add = step_add;
+    return k;
+  }
+  static int sample_uniform(float* out, int64_t n, float lo, float hi, unsigned long long seed, uint32_t stream_id,
+                            const long long* step_dev, long long step_add, void* stream) {
+    if (n <= 0) return fail(DGMK_EINVAL, "need n > 0");
+    BK bk(stream);
+    const void* ptrs[] = {out};
+    if (int r = check_common(bk, ptrs, 1, 1, 1)) return r;
+    if (step_dev && !bk.is_device_ptr(step_dev)) return fail(DGMK_EDEVICE, "step counter must be device memory");
+    PhiloxUniformFn f; f.out = out; f.n = n; f.lo = lo; f.span = hi - lo; f.stream_id = stream_id;
+    f.key = philox_key(seed, step_dev, step_add);
+    bk.ew(f, (n + 3) / 4);
+    return finish(bk);
+  }
+  static int sample_heat(float* X, float* X0, float* XBD1, float* XBD2, int64_t B, float xmax, float tmax, float xbd2,
+                         unsigned long long seed, const long long* step_dev, long long step_add, void* stream) {
+    if (B <= 0) return fail(DGMK_EINVAL, "need B > 0");
+    BK bk(stream);
+    const void* ptrs[] = {X, X0, XBD1, XBD2};
+    if (int r = check_common(bk, ptrs, 4, 1, 1)) return r;
+    if (step_dev && !bk.is_device_ptr(step_dev)) return fail(DGMK_EDEVICE, "step counter must be device memory");
+    PhiloxHeatFn f; f.X = X; f.X0 = X0; f.XBD1 = XBD1; f.XBD2 = XBD2; f.B = B; f.xmax = xmax; f.tmax = tmax; f.xbd2 = xbd2;
+    f.key = philox_key(seed, step_dev, step_add);
+    bk.ew(f, (B + 3) / 4);
+    return finish(bk);
+  }
 };
 
 inline int param_layout(const dgmk_net_desc* desc, int32_t index, int64_t* offset, int32_t* rows, int32_t* cols, int32_t* live) {
@@ -423,4 +452,11 @@ inline size_t workspace_bytes(const dgmk_net_desc* desc, int32_t cls, int64_t B,
   int dgmk_adam_dev(float* th, float* m, float* v, const float* g, const uint8_t* live, int64_t P, double lr,      \
                     double b1, double b2, double eps, long long* state, void* st) {                                \
     return dgmk::Api<BK>::adam_dev(th, m, v, g, live, P, lr, b1, b2, eps, state, st); }                            \
+  int dgmk_sample_uniform(float* out, int64_t n, float lo, float hi, unsigned long long seed, uint32_t stream_id,  \
+                          const long long* step_dev, long long step_add, void* st) {                               \
+    return dgmk::Api<BK>::sample_uniform(out, n, lo, hi, seed, stream_id, step_dev, step_add, st); }               \
+  int dgmk_sample_heat(float* X, float* X0, float* XBD1, float* XBD2, int64_t B, float xmax, float tmax,           \
+                       float xbd2, unsigned long long seed, const long long* step_dev, long long step_add,         \
+                       void* st) {                                                                                 \
+    return dgmk::Api<BK>::sample_heat(X, X0, XBD1, XBD2, B, xmax, tmax, xbd2, seed, step_dev, step_add, st); }     \
   }

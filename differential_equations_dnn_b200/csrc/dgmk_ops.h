@@ -693,6 +693,73 @@ struct AdamFn {
   }
 };
 
+// ================================ on-device collocation sampler =====================
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11; Random123 philox4x32_R(10, ...)): counter-based, so a sample is a
+// pure function of (seed, stream, step, element) -- no generator state to carry through a CUDA graph.  Replaces the
+// torch.rand / rand_like draws of the reference drivers (heat.py:125-126, simple_ode.py:91, fitzhugh_nagumo.py:129,
+// fredholm.py:67,100) when the driver is asked for sampler="philox"; bit-exact oracle: oracle/philox_np.py.
+DGMK_HD void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    c[1] = (uint32_t)p1; c[3] = (uint32_t)p0; c[0] = n0; c[2] = n2;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+// u in [0, 1) with 24 random bits; value = fl(fl(span * u) + lo) (two roundings: no FMA contraction, so that the
+// numpy oracle reproduces every bit)
+DGMK_HD float philox_value(uint32_t w, float lo, float span) {
+  const float u = (float)(w >> 8) * 5.9604644775390625e-8f;
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(__fmul_rn(span, u), lo);
+#else
+  volatile float t = span * u;
+  return t + lo;
+#endif
+}
+// block b of stream `stream_id` at step (*step_dev + step_add): words for elements 4b .. 4b+3
+struct PhiloxKey {
+  uint32_t k0, k1; const long long* step_dev; long long step_add;
+  DGMK_HD void block(int64_t b, uint32_t stream_id, uint32_t (&c)[4]) const {
+    const long long step = step_add + (step_dev ? *step_dev : 0);
+    c[0] = (uint32_t)b; c[1] = (uint32_t)((uint64_t)b >> 32); c[2] = (uint32_t)step; c[3] = stream_id;
+    philox4x32_10(c, k0, k1);
+  }
+};
+// out[i] = lo + span * u_i; one item = four consecutive elements
+struct PhiloxUniformFn {
+  float* out; int64_t n; float lo, span; uint32_t stream_id; PhiloxKey key;
+  DGMK_HD void operator()(int64_t b) const {
+    uint32_t c[4];
+    key.block(b, stream_id, c);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (4 * b + q < n) out[4 * b + q] = philox_value(c[q], lo, span);
+  }
+};
+// the four operand blocks of a heat step (heat.py:125-134): x = xmax u (stream 0), t = tmax u' (stream 1);
+// X = [x, t], X0 = [x, 0], XBD1 = [0, t], XBD2 = [xbd2, t]; one item = four consecutive points
+struct PhiloxHeatFn {
+  float* X; float* X0; float* XBD1; float* XBD2; int64_t B; float xmax, tmax, xbd2; PhiloxKey key;
+  DGMK_HD void operator()(int64_t b) const {
+    uint32_t cx[4], ct[4];
+    key.block(b, 0u, cx);
+    key.block(b, 1u, ct);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t i = 4 * b + q;
+      if (i < B) {
+        const float x = philox_value(cx[q], 0.f, xmax), t = philox_value(ct[q], 0.f, tmax);
+        X[2 * i] = x; X[2 * i + 1] = t;
+        X0[2 * i] = x; X0[2 * i + 1] = 0.f;
+        XBD1[2 * i] = 0.f; XBD1[2 * i + 1] = t;
+        XBD2[2 * i] = xbd2; XBD2[2 * i + 1] = t;
+      }
+    }
+  }
+};
+
 // Device-resident step counter variant (CUDA-graph capturable training loops): state = 16 bytes,
 // [int64 step | float lr/(1-b1^t) | float sqrt(1-b2^t)].  AdamPrepFn (one thread) advances the
 // counter and forms the two bias-correction scalars in doubles exactly like torch does on the host;

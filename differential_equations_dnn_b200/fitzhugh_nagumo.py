@@ -12,6 +12,7 @@ from ._loop import graphed_loop, print_progress
 from .auxiliary_funs import fn_timer
 from .heat import _device
 from .optim import FusedAdam
+from .sampler import PhiloxSampler
 from .simple_ode import _require_calls
 
 IEXT, ALPHA, BETA, TAU = 0.5, 0.7, 0.8, 2.5  # fitzhugh_nagumo.py:69-70
@@ -34,8 +35,11 @@ def dgm_loss_func(y, y0, t, y_ic):
 def minimize_loss_dgm(net, y_ic, iterations=1000, batch_size=32, lrate=1e-4, sampler="grid", cuda_graph=False):
     """fitzhugh_nagumo.py:100-156.  sampler="grid" is the shipped one: `batch_size` (<=200)
     distinct nodes of a 200-point grid on [0,30] (:123-133); sampler="uniform" is the
-    commented-out `30.01 * rand` (:129), the only one that scales past 200 rows.
+    commented-out `30.01 * rand` (:129), the only one that scales past 200 rows; sampler="philox" is that uniform
+    draw from this library's on-device Philox sampler (`sampler.PhiloxSampler`, one launch).
     `cuda_graph=True` (single GPU): one captured iteration replayed (`_loop.graphed_loop`)."""
+    if sampler not in ("grid", "uniform", "philox"):
+        raise ValueError("sampler must be 'grid', 'uniform' or 'philox'")
     device = _device()
     parallel.sync_parameters(net)            # data parallel: rank 0's weights everywhere
     gen = parallel.sampler_generator(device)  # ... and per-rank rows (None on one GPU: the default RNG stream)
@@ -46,7 +50,12 @@ def minimize_loss_dgm(net, y_ic, iterations=1000, batch_size=32, lrate=1e-4, sam
     T = torch.linspace(0.0, 30.0, steps=num_samples, device=device)
     prob = torch.full((num_samples,), 1.0 / num_samples, device=device)
 
-    def sample():
+    ps = PhiloxSampler(device) if sampler == "philox" else None
+    tp = torch.empty([batch_size, 1], device=device) if ps is not None else None
+
+    def sample(i=0):
+        if ps is not None:
+            return ps.uniform(tp, 0.0, 30.01, step_add=i)
         if sampler == "grid":
             return T[prob.multinomial(num_samples=batch_size, replacement=False, generator=gen)].reshape(-1, 1)
         return 30.01 * torch.rand([batch_size, 1], device=device, generator=gen)
@@ -61,12 +70,12 @@ def minimize_loss_dgm(net, y_ic, iterations=1000, batch_size=32, lrate=1e-4, sam
             loss.backward()
             optimizer.step()
             return loss
-        train_loss = graphed_loop(step, iterations, device)
+        train_loss = graphed_loop(step, iterations, device, counter=None if ps is None else ps.step)
         print_progress(train_loss, lrate, parallel.rank())
         return net, train_loss
     losses = []
     for i in range(iterations):
-        t = sample()
+        t = sample(i)
         optimizer.zero_grad()
         with deferred_forward(net):
             y, y0 = net(t), net(t0)

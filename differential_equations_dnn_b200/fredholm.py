@@ -13,6 +13,7 @@ from ._loop import graphed_loop, print_progress
 from .auxiliary_funs import fn_timer
 from .heat import _device
 from .optim import FusedAdam
+from .sampler import PhiloxSampler
 
 
 def exact_solution(x):
@@ -42,30 +43,48 @@ def dgm_loss_func(net, x, k=50, nodes=None):
 
 
 @fn_timer
-def minimize_loss_dgm(net, y_ic=2.0, iterations=1000, batch_size=32, lrate=1e-4, k=50, cuda_graph=False):
+def minimize_loss_dgm(net, y_ic=2.0, iterations=1000, batch_size=32, lrate=1e-4, k=50, cuda_graph=False, sampler="torch"):
     """fredholm.py:77-117 (y_ic is accepted and unused, as there).
-    `cuda_graph=True` (single GPU): one captured iteration replayed (`_loop.graphed_loop`)."""
+    `cuda_graph=True` (single GPU): one captured iteration replayed (`_loop.graphed_loop`).
+    sampler="philox": the points and the k node sets come from this library's on-device Philox sampler
+    (`sampler.PhiloxSampler`): 2 launches per step instead of the reference's 2 k + 3 (k rand_like, k multiplies, a stack);
+    statistically equivalent draws, not torch's stream."""
+    if sampler not in ("torch", "philox"):
+        raise ValueError("sampler must be 'torch' or 'philox'")
     device = _device()
     parallel.sync_parameters(net)            # data parallel: rank 0's weights everywhere
     gen = parallel.sampler_generator(device)  # ... and per-rank rows (None on one GPU: the default RNG stream)
     graphed = cuda_graph and not parallel.is_enabled()
     optimizer = FusedAdam(net.parameters(), lr=lrate, capturable=graphed)
+    ps = PhiloxSampler(device) if sampler == "philox" else None
+    if ps is not None:
+        tp = torch.empty([batch_size, 1], device=device)
+        nodes_p = torch.empty([k, batch_size, 1], device=device)
+
+    def draw(i=0):   # -> (points, nodes or None)
+        if ps is not None:
+            ps.uniform(tp, 0.0, np.pi / 2.0, stream_id=0, step_add=i)
+            ps.uniform(nodes_p, 0.0, np.pi / 2.0, stream_id=1, step_add=i)
+            return tp, nodes_p
+        t = np.pi / 2.0 * torch.rand([batch_size, 1], device=device, generator=gen)
+        return t, (None if gen is None else draw_nodes(t, k, gen))
+
     if graphed:
         def step():
-            t = np.pi / 2.0 * torch.rand([batch_size, 1], device=device, generator=gen)
+            t, nodes = draw()
             optimizer.zero_grad()
-            loss = dgm_loss_func(net, t, k)
+            loss = dgm_loss_func(net, t, k, nodes=nodes)
             loss.backward()
             optimizer.step()
             return loss
-        train_loss = graphed_loop(step, iterations, device)
+        train_loss = graphed_loop(step, iterations, device, counter=None if ps is None else ps.step)
         print_progress(train_loss, lrate, parallel.rank())
         return net, train_loss
     losses = []
     for i in range(iterations):
-        t = np.pi / 2.0 * torch.rand([batch_size, 1], device=device, generator=gen)
+        t, nodes = draw(i)
         optimizer.zero_grad()
-        loss = dgm_loss_func(net, t, k, nodes=None if gen is None else draw_nodes(t, k, gen))
+        loss = dgm_loss_func(net, t, k, nodes=nodes)
         loss.backward()
         optimizer.step()
         losses.append(loss.detach())

@@ -14,6 +14,7 @@ from ._flat import DeferredOutput, FlatParamModule, deferred_forward  # noqa: F4
 from ._loop import graphed_loop, print_progress
 from .auxiliary_funs import fn_timer
 from .optim import FusedAdam
+from .sampler import PhiloxSampler
 
 
 def _device():
@@ -38,9 +39,10 @@ def dgm_loss_func(net, x, x0, xbd1, xbd2, x_bd1, x_bd2):
     return ag.HeatStepFn.apply(net, x, x0, xbd1, xbd2, x_bd1, x_bd2, 1.0, *ag.params_of(net))
 
 
-def _minimize_graphed(net, iterations, batch_size, lrate, warmup=11, xbd2_value=torch.pi):
+def _minimize_graphed(net, iterations, batch_size, lrate, warmup=11, xbd2_value=torch.pi, sampler="torch"):
     """The training loop with one captured iteration replayed (`_loop.graphed_loop`): same RNG stream,
-    same arithmetic as the eager loop."""
+    same arithmetic as the eager loop (sampler="torch"), or the four operand blocks drawn by ONE launch of the
+    on-device Philox sampler (sampler="philox", SURVEY 8f N2: 8 sampler launches per iteration become 1)."""
     device = _device()
     parallel.sync_parameters(net)            # data parallel: rank 0's weights everywhere
     gen = parallel.sampler_generator(device)  # ... and per-rank rows (None on one GPU: the default RNG stream)
@@ -50,26 +52,35 @@ def _minimize_graphed(net, iterations, batch_size, lrate, warmup=11, xbd2_value=
     xbd2x = torch.ones([batch_size, 1], device=device) * xbd2_value
     xbd2y = torch.zeros([batch_size, 1], device=device)
 
+    ps = PhiloxSampler(device) if sampler == "philox" else None
+    if ps is not None:
+        PX, PX0, PB1, PB2 = (torch.empty([batch_size, 2], device=device) for _ in range(4))
+
     def step():
-        x = torch.pi * torch.rand([batch_size, 1], device=device, generator=gen)
-        t = 3.0 * torch.rand([batch_size, 1], device=device, generator=gen)
-        X = torch.cat([x, t], dim=1)
-        X0 = torch.cat([x, t0], dim=1)
-        X_BD1 = torch.cat([xbd1, t], dim=1)
-        X_BD2 = torch.cat([xbd2x, t], dim=1)
+        if ps is not None:
+            ps.heat(PX, PX0, PB1, PB2, torch.pi, 3.0, xbd2_value)
+            X, X0, X_BD1, X_BD2 = PX, PX0, PB1, PB2
+        else:
+            x = torch.pi * torch.rand([batch_size, 1], device=device, generator=gen)
+            t = 3.0 * torch.rand([batch_size, 1], device=device, generator=gen)
+            X = torch.cat([x, t], dim=1)
+            X0 = torch.cat([x, t0], dim=1)
+            X_BD1 = torch.cat([xbd1, t], dim=1)
+            X_BD2 = torch.cat([xbd2x, t], dim=1)
         optimizer.zero_grad()
         loss = dgm_loss_func(net, X, X0, X_BD1, X_BD2, xbd1, xbd2y)
         loss.backward()
         optimizer.step()
         return loss
 
-    train_loss = graphed_loop(step, iterations, device, warmup)
+    train_loss = graphed_loop(step, iterations, device, warmup, counter=None if ps is None else ps.step)
     print_progress(train_loss, lrate, parallel.rank())
     return net, train_loss
 
 
 @fn_timer
-def minimize_loss_dgm(net, iterations=1000, batch_size=32, lrate=1e-4, cuda_graph=False, xbd2_value=torch.pi):
+def minimize_loss_dgm(net, iterations=1000, batch_size=32, lrate=1e-4, cuda_graph=False, xbd2_value=torch.pi,
+                      sampler="torch"):
     """The reference's training driver (heat.py:98-149): same sampler, same Adam
     defaults, returns (net, train_loss: list[float]).  Differences that do not change
     results: losses stay on the device and are read back once at the end (plus every
@@ -77,9 +88,13 @@ def minimize_loss_dgm(net, iterations=1000, batch_size=32, lrate=1e-4, cuda_grap
     `parallel.enable_data_parallel()` rank 0's weights are broadcast first, each rank draws its own
     rows from a per-rank generator (`parallel.sampler_generator`) and the gradient is all-reduced
     inside `dgm_loss_func`.  `cuda_graph=True` (single GPU) replays one captured
-    iteration instead of launching it from Python (`_minimize_graphed`)."""
+    iteration instead of launching it from Python (`_minimize_graphed`).  sampler="philox": the collocation points
+    come from this library's on-device Philox sampler (one launch per step; `sampler.PhiloxSampler`) instead of
+    torch.rand -- statistically equivalent draws, not torch's stream."""
+    if sampler not in ("torch", "philox"):
+        raise ValueError("sampler must be 'torch' or 'philox'")
     if cuda_graph and not parallel.is_enabled():
-        return _minimize_graphed(net, iterations, batch_size, lrate, xbd2_value=xbd2_value)
+        return _minimize_graphed(net, iterations, batch_size, lrate, xbd2_value=xbd2_value, sampler=sampler)
     device = _device()
     parallel.sync_parameters(net)            # data parallel: rank 0's weights everywhere
     gen = parallel.sampler_generator(device)  # ... and per-rank rows (None on one GPU: the default RNG stream)
@@ -89,13 +104,19 @@ def minimize_loss_dgm(net, iterations=1000, batch_size=32, lrate=1e-4, cuda_grap
     xbd2x = torch.ones([batch_size, 1], device=device) * xbd2_value
     xbd2y = torch.zeros([batch_size, 1], device=device)
     losses = []
+    ps = PhiloxSampler(device) if sampler == "philox" else None
+    if ps is not None:
+        X, X0, X_BD1, X_BD2 = (torch.empty([batch_size, 2], device=device) for _ in range(4))
     for i in range(iterations):
-        x = torch.pi * torch.rand([batch_size, 1], device=device, generator=gen)
-        t = 3.0 * torch.rand([batch_size, 1], device=device, generator=gen)
-        X = torch.cat([x, t], dim=1)
-        X0 = torch.cat([x, t0], dim=1)
-        X_BD1 = torch.cat([xbd1, t], dim=1)
-        X_BD2 = torch.cat([xbd2x, t], dim=1)
+        if ps is not None:
+            ps.heat(X, X0, X_BD1, X_BD2, torch.pi, 3.0, xbd2_value, step_add=i)
+        else:
+            x = torch.pi * torch.rand([batch_size, 1], device=device, generator=gen)
+            t = 3.0 * torch.rand([batch_size, 1], device=device, generator=gen)
+            X = torch.cat([x, t], dim=1)
+            X0 = torch.cat([x, t0], dim=1)
+            X_BD1 = torch.cat([xbd1, t], dim=1)
+            X_BD2 = torch.cat([xbd2x, t], dim=1)
         optimizer.zero_grad()
         loss = dgm_loss_func(net, X, X0, X_BD1, X_BD2, xbd1, xbd2y)
         loss.backward()

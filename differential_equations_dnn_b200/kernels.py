@@ -237,3 +237,37 @@ def adam_step_dev(theta, m, v, grad, live, lr, beta1, beta2, eps, state):
         rc = lib.dgmk_adam_dev(_ptr(theta), _ptr(m), _ptr(v), _ptr(grad), _ptr(live), theta.numel(), float(lr),
                                float(beta1), float(beta2), float(eps), _ptr(state), _stream(theta.device))
     _cabi.check(rc, lib)
+
+
+def _step_ptr(step):
+    if step is None:
+        return None
+    if not (step.is_cuda and step.dtype == torch.int64 and step.numel() >= 1):
+        raise DgmkError("the sampler's step counter must be a CUDA int64 tensor")
+    return _ptr(step)
+
+
+def sample_uniform(out, lo, hi, seed, stream_id=0, step=None, step_add=0):
+    """out[...] = lo + (hi - lo) * u, u ~ U[0, 1) from Philox4x32-10 (include/dgmk.h: dgmk_sample_uniform; bit-exact oracle
+    oracle/philox_np.py).  `step`: device int64 counter read by the kernel (CUDA-graph replays), plus `step_add`."""
+    _dev_f32(out)
+    lib = _cabi.load()
+    with torch.cuda.device(out.device):
+        rc = lib.dgmk_sample_uniform(_ptr(out), out.numel(), float(lo), float(hi), int(seed) & (2 ** 64 - 1), int(stream_id),
+                                     _step_ptr(step), int(step_add), _stream(out.device))
+    _cabi.check(rc, lib)
+    return out
+
+
+def sample_heat(X, X0, XBD1, XBD2, xmax, tmax, xbd2, seed, step=None, step_add=0):
+    """The four [B, 2] operand blocks of a heat step (heat.py:125-134) in one launch (dgmk_sample_heat)."""
+    _dev_f32(X, X0, XBD1, XBD2)
+    B = X.shape[0]
+    for t in (X, X0, XBD1, XBD2):
+        if tuple(t.shape) != (B, 2):
+            raise DgmkError("sample_heat needs four [B, 2] tensors")
+    lib = _cabi.load()
+    with torch.cuda.device(X.device):
+        rc = lib.dgmk_sample_heat(_ptr(X), _ptr(X0), _ptr(XBD1), _ptr(XBD2), B, float(xmax), float(tmax), float(xbd2),
+                                  int(seed) & (2 ** 64 - 1), _step_ptr(step), int(step_add), _stream(X.device))
+    _cabi.check(rc, lib)

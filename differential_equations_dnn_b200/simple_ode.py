@@ -13,6 +13,7 @@ from ._loop import graphed_loop, print_progress
 from .auxiliary_funs import fn_timer
 from .heat import _device
 from .optim import FusedAdam
+from .sampler import PhiloxSampler
 
 
 def exact_solution(t):
@@ -53,9 +54,13 @@ def dgm_loss_func(y, y0, t, y_ic):
 
 
 @fn_timer
-def minimize_loss_dgm(net, y_ic=2.0, iterations=1000, batch_size=32, lrate=1e-4, cuda_graph=False):
+def minimize_loss_dgm(net, y_ic=2.0, iterations=1000, batch_size=32, lrate=1e-4, cuda_graph=False, sampler="torch"):
     """simple_ode.py:66-112: t ~ 1.01 U[0,1), Adam(lr); returns (net, list[float]).
-    `cuda_graph=True` (single GPU): one captured iteration replayed (`_loop.graphed_loop`)."""
+    `cuda_graph=True` (single GPU): one captured iteration replayed (`_loop.graphed_loop`).
+    sampler="philox": t comes from this library's on-device Philox sampler (`sampler.PhiloxSampler`; statistically
+    equivalent draws, one launch) instead of torch.rand."""
+    if sampler not in ("torch", "philox"):
+        raise ValueError("sampler must be 'torch' or 'philox'")
     device = _device()
     parallel.sync_parameters(net)            # data parallel: rank 0's weights everywhere
     gen = parallel.sampler_generator(device)  # ... and per-rank rows (None on one GPU: the default RNG stream)
@@ -63,9 +68,17 @@ def minimize_loss_dgm(net, y_ic=2.0, iterations=1000, batch_size=32, lrate=1e-4,
     optimizer = FusedAdam(net.parameters(), lr=lrate, capturable=graphed)
     y_ic = torch.ones([batch_size, 1], device=device) * y_ic
     t0 = torch.zeros([batch_size, 1], device=device)
+    ps = PhiloxSampler(device) if sampler == "philox" else None
+    tp = torch.empty([batch_size, 1], device=device) if ps is not None else None
+
+    def draw(i=0):
+        if ps is not None:
+            return ps.uniform(tp, 0.0, 1.01, step_add=i)
+        return 1.01 * torch.rand([batch_size, 1], device=device, generator=gen)
+
     if graphed:
         def step():
-            t = 1.01 * torch.rand([batch_size, 1], device=device, generator=gen)
+            t = draw()
             optimizer.zero_grad()
             with deferred_forward(net):
                 y, y0 = net(t), net(t0)
@@ -73,12 +86,12 @@ def minimize_loss_dgm(net, y_ic=2.0, iterations=1000, batch_size=32, lrate=1e-4,
             loss.backward()
             optimizer.step()
             return loss
-        train_loss = graphed_loop(step, iterations, device)
+        train_loss = graphed_loop(step, iterations, device, counter=None if ps is None else ps.step)
         print_progress(train_loss, lrate, parallel.rank())
         return net, train_loss
     losses = []
     for i in range(iterations):
-        t = 1.01 * torch.rand([batch_size, 1], device=device, generator=gen)
+        t = draw(i)
         optimizer.zero_grad()
         with deferred_forward(net):
             y, y0 = net(t), net(t0)

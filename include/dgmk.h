@@ -133,6 +133,21 @@ int dgmk_adam(float* theta, float* m, float* v, const float* grad, const uint8_t
 int dgmk_adam_dev(float* theta, float* m, float* v, const float* grad, const uint8_t* live, int64_t P,
                   double lr, double beta1, double beta2, double eps, long long* state, void* stream);
 
+/* ---- on-device collocation sampler ---------------------------------------
+ * Replaces the torch.rand / rand_like draws of the reference drivers (heat.py:125-126, simple_ode.py:91,
+ * fitzhugh_nagumo.py:129, fredholm.py:67,100) with ONE launch per step of a counter-based generator, Philox4x32-10
+ * (Salmon et al., SC'11): element i takes word i % 4 of the block with counter (lo32(i/4), hi32(i/4), lo32(step),
+ * stream_id) under key (lo32(seed), hi32(seed)); u = (word >> 8) * 2^-24 in [0,1); value = lo + (hi - lo) * u
+ * (two FP32 roundings).  step = *step_dev + step_add; step_dev (device int64, may be NULL) lets a captured CUDA graph
+ * draw fresh points on every replay with no host work.  Statistical, not bitwise, parity with torch's stream; the
+ * generator itself is pinned bit for bit by oracle/philox_np.py (Random123 known-answer vectors). */
+int dgmk_sample_uniform(float* out, int64_t n, float lo, float hi, unsigned long long seed, uint32_t stream_id,
+                        const long long* step_dev, long long step_add, void* stream);
+/* heat.py:125-134 in one launch: x = xmax*u (stream 0), t = tmax*u' (stream 1); X = [x,t], X0 = [x,0],
+ * XBD1 = [0,t], XBD2 = [xbd2,t], each [B,2] */
+int dgmk_sample_heat(float* X, float* X0, float* XBD1, float* XBD2, int64_t B, float xmax, float tmax, float xbd2,
+                     unsigned long long seed, const long long* step_dev, long long step_add, void* stream);
+
 /* ---- diagnostics used by bench.py (not reference-facing) --------------------------- */
 unsigned long long dgmk_launch_count(void); /* kernels launched by this library so far */
 int dgmk_ffma_probe(const float* in, float* out, int blocks, int iters, void* stream);

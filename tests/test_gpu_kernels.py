@@ -338,3 +338,44 @@ def test_tile_step_vs_layerwise_and_oracle(K, case):
     finally:
         lib.dgmk_set_tile_engine(1)
     assert np.array_equal(again, out["tile"])
+
+
+# ------------------------------------------------------------------------------------------------
+# On-device collocation sampler: the CUDA kernels against oracle/philox_np.py, bit for bit.
+@pytest.mark.parametrize("n,lo,hi,seed,stream,step_dev,step_add", [
+    (1, 0.0, 1.0, 0, 0, None, 0), (7, 0.0, 1.01, 1234, 0, None, 5), (64, -2.0, 3.5, 2 ** 63 + 12345, 9, 41, 1),
+    (100003, 0.0, np.pi / 2, 2 ** 40 + 3, 257, 2 ** 33 + 5, 0), (50 * 32, 0.0, np.pi / 2, 7, 1, 3, 0)])
+def test_philox_uniform_kernel_is_bit_exact(K, n, lo, hi, seed, stream, step_dev, step_add):
+    from oracle import philox_np as PH
+    out = torch.full([n + 5], float("nan"), device="cuda")
+    step = None if step_dev is None else torch.tensor([step_dev], dtype=torch.int64, device="cuda")
+    K.sample_uniform(out[:n], lo, hi, seed, stream, step, step_add)
+    got = out.cpu().numpy()
+    assert np.array_equal(got[:n], PH.uniform(n, lo, hi, seed, stream, (step_dev or 0) + step_add))
+    assert np.all(np.isnan(got[n:]))
+
+
+@pytest.mark.parametrize("B", [1, 6, 64, 4099])
+def test_philox_heat_kernel_is_bit_exact(K, B):
+    from oracle import philox_np as PH
+    bufs = [torch.full([B, 2], float("nan"), device="cuda") for _ in range(4)]
+    step = torch.tensor([17], dtype=torch.int64, device="cuda")
+    K.sample_heat(*bufs, np.pi, 3.0, np.pi, 99, step, 2)
+    for got, want in zip(bufs, PH.heat(B, np.pi, 3.0, np.pi, 99, 19)):
+        assert np.array_equal(got.cpu().numpy(), want)
+    # a captured graph draws fresh points on every replay: the kernel reads the counter from device memory
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        K.sample_heat(*bufs, np.pi, 3.0, np.pi, 99, step, 0)
+    torch.cuda.current_stream().wait_stream(s)
+    with torch.cuda.graph(g, stream=s):
+        K.sample_heat(*bufs, np.pi, 3.0, np.pi, 99, step, 0)
+        step.add_(1)
+    for it in range(3):
+        g.replay()
+        torch.cuda.synchronize()
+        assert np.array_equal(bufs[0].cpu().numpy(), PH.heat(B, np.pi, 3.0, np.pi, 99, 17 + it)[0])
+    with pytest.raises(K.DgmkError):
+        K.sample_uniform(torch.zeros(4), 0.0, 1.0, 0)   # host tensor: no CPU path

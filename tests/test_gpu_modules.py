@@ -442,3 +442,53 @@ def test_eval_and_jets_hidden128(kind):
     assert rel(J.detach().double().cpu().numpy(), J64[:, 0, :]) < TOL
     (Jx,) = torch.autograd.grad(J[:, 0], Xg, grad_outputs=torch.ones_like(J[:, 0]), create_graph=True)
     assert rel(Jx[:, 0].detach().double().cpu().numpy(), H64[:, 0, 0, 0]) < TOL
+
+
+@pytest.mark.parametrize("problem", ["heat", "simple_ode", "fhn", "fredholm"])
+def test_philox_sampler_drivers(problem):
+    """sampler="philox" (SURVEY 8f N2): the collocation points of every `minimize_loss_dgm` come from ONE launch of this
+    library's counter-based sampler.  A draw is a pure function of (seed, stream, iteration), so the eager loop
+    (iteration passed from the host) and the CUDA-graph loop (iteration read from the device counter the replay
+    advances) see the same points: the trajectories agree like the torch-sampler ones do, and training makes
+    progress."""
+    from differential_equations_dnn_b200 import dgm_net, neural_networks, heat, simple_ode, fitzhugh_nagumo, fredholm
+    its = 60
+    curves = []
+    for graph in (False, True):
+        torch.manual_seed(1234)
+        if problem == "heat":
+            net = dgm_net.DGM(input_dim=2, output_dim=1, hidden_size=32, num_layers=1).cuda()
+            _, loss = heat.minimize_loss_dgm(net, iterations=its, batch_size=64, lrate=1e-3, cuda_graph=graph, sampler="philox")
+        elif problem == "simple_ode":
+            net = neural_networks.MLP(input_dim=1, output_dim=1, hidden_size=32).cuda()
+            _, loss = simple_ode.minimize_loss_dgm(net, y_ic=2.0, iterations=its, batch_size=64, lrate=1e-3, cuda_graph=graph,
+                                                   sampler="philox")
+        elif problem == "fhn":
+            net = neural_networks.MLP(input_dim=1, output_dim=2, hidden_size=32, num_layers=2, activation="tanh").cuda()
+            _, loss = fitzhugh_nagumo.minimize_loss_dgm(net, torch.zeros([64, 2], device="cuda"), iterations=its, batch_size=64,
+                                                        lrate=1e-3, sampler="philox", cuda_graph=graph)
+        else:
+            net = neural_networks.DGM(input_dim=1, output_dim=1, hidden_size=32).cuda()
+            _, loss = fredholm.minimize_loss_dgm(net, iterations=its, batch_size=32, lrate=1e-3, k=8, cuda_graph=graph,
+                                                 sampler="philox")
+        assert len(loss) == its and np.all(np.isfinite(loss))
+        assert torch.isfinite(net.flat_theta()).all()
+        curves.append(np.array(loss))
+    eager, graphed = curves
+    assert np.allclose(eager[:15], graphed[:15], rtol=1e-4), (eager[:15], graphed[:15])
+    assert abs(eager[-10:].mean() - graphed[-10:].mean()) <= 0.25 * abs(eager[-10:].mean()) + 1e-6
+    assert graphed[-10:].mean() < graphed[:10].mean()
+
+
+def test_simple_ode_end_to_end_philox_graph():
+    """BASELINE config 1 end to end with the on-device sampler and the CUDA-graph driver: 5000 its x 64, MAE vs
+    2 exp(-t) on 25 nodes within 1e-3 of the reference's 0.00253 (statistical parity of the sampler)."""
+    from differential_equations_dnn_b200 import neural_networks as nn_, simple_ode
+    torch.manual_seed(0)
+    net = nn_.MLP(input_dim=1, output_dim=1, hidden_size=32).cuda()
+    net, losses = simple_ode.minimize_loss_dgm(net, y_ic=2.0, iterations=5000, batch_size=64, lrate=1e-4, cuda_graph=True,
+                                               sampler="philox")
+    assert len(losses) == 5000 and losses[-1] < losses[0]
+    sol = simple_ode.gridEvaluation(net, nodes=25)
+    mae = np.abs(sol - simple_ode.exact_solution(np.linspace(0, 1.0, 25))).mean()
+    assert mae < 0.00253 + 1e-3, mae

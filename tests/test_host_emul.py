@@ -211,3 +211,34 @@ def test_rev1_units_per_thread_variant_is_bit_identical(lib, cs, tanh_gates, V):
     lib.dgmk_emul_check_rev1_runv.restype = C.c_int
     lib.dgmk_emul_check_rev1_runv.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint]
     assert lib.dgmk_emul_check_rev1_runv(cs, tanh_gates, V, 37, 5) == 0
+
+
+@pytest.mark.parametrize("n,lo,hi,seed,stream,step_dev,step_add", [
+    (1, 0.0, 1.0, 0, 0, None, 0), (7, 0.0, 1.01, 1234, 0, None, 5), (64, -2.0, 3.5, 2 ** 63 + 12345, 9, 41, 1),
+    (1003, 0.0, np.pi / 2, 2 ** 40 + 3, 257, 2 ** 33 + 5, 0)])
+def test_philox_uniform_functor_is_bit_exact(lib, n, lo, hi, seed, stream, step_dev, step_add):
+    """PhiloxUniformFn (csrc/dgmk_ops.h, the code dgmk_sample_uniform launches) compiled for the host against
+    oracle/philox_np.py: ragged tails, non-zero lo, 64-bit seeds, the step read through the device pointer."""
+    from oracle import philox_np as PH
+    out = np.full(n + 3, np.nan, np.float32)
+    sd = np.array([step_dev if step_dev is not None else 0], np.int64)
+    rc = lib.dgmk_sample_uniform(P(out), n, lo, hi, seed, stream, P(sd) if step_dev is not None else None, step_add, None)
+    assert rc == 0
+    want = PH.uniform(n, lo, hi, seed, stream, (step_dev or 0) + step_add)
+    assert np.array_equal(out[:n], want)
+    assert np.all(np.isnan(out[n:]))   # nothing written past n
+
+
+@pytest.mark.parametrize("B", [1, 6, 64, 203])
+def test_philox_heat_functor_is_bit_exact(lib, B):
+    from oracle import philox_np as PH
+    bufs = [np.full((B + 1, 2), np.nan, np.float32) for _ in range(4)]
+    sd = np.array([17], np.int64)
+    rc = lib.dgmk_sample_heat(P(bufs[0]), P(bufs[1]), P(bufs[2]), P(bufs[3]), B, np.pi, 3.0, np.pi, 99, P(sd), 2, None)
+    assert rc == 0
+    for got, want in zip(bufs, PH.heat(B, np.pi, 3.0, np.pi, 99, 19)):
+        assert np.array_equal(got[:B], want)
+        assert np.all(np.isnan(got[B:]))
+    X, X0, B1, B2 = (b[:B] for b in bufs)
+    assert X[:, 0].max() < np.float32(np.pi) + 1e-6 and X[:, 1].max() < 3.0 and X.min() >= 0.0
+    assert np.array_equal(X0[:, 0], X[:, 0]) and np.array_equal(B1[:, 1], X[:, 1]) and np.all(B2[:, 0] == np.float32(np.pi))

@@ -98,3 +98,28 @@ def test_known_answers():
     tt = np.linspace(0, np.pi / 2, 200001)
     integral = np.trapezoid(np.cos(tt) * 2 * np.sin(tt), tt)
     assert abs(integral - 1.0) < 1e-9
+
+
+def test_philox_kat():
+    """oracle/philox_np.py against the known-answer vectors of Random123 (kat_vectors, philox4x32-10): the pin of the
+    on-device sampler's generator (the CUDA kernel is compared with this oracle bit for bit in the -m gpu tests, the
+    same functor compiled for the host in tests/test_host_emul.py)."""
+    from oracle import philox_np as P
+    kats = [
+        ([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+        ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+        ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0], [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+    ]
+    for ctr, key, want in kats:
+        got = P.philox4x32_10(np.array(ctr, dtype=np.uint32), np.array(key, dtype=np.uint32))
+        assert [int(v) for v in got] == want
+    # stream layout: element i = word i % 4 of block i // 4; streams and steps are independent; u in [0, 1)
+    w = P.words(10, seed=0x0123456789abcdef, stream_id=3, step=7)
+    blk = P.philox4x32_10(np.array([[0, 0, 7, 3], [1, 0, 7, 3], [2, 0, 7, 3]], dtype=np.uint32),
+                          np.array([[0x89abcdef, 0x01234567]], dtype=np.uint32)).reshape(-1)
+    assert np.array_equal(w, blk[:10])
+    u = P.uniform(100000, 0.0, 1.0, seed=5, stream_id=0, step=0)
+    assert u.dtype == np.float32 and u.min() >= 0.0 and u.max() < 1.0
+    assert abs(u.mean() - 0.5) < 5e-3 and abs(u.var() - 1 / 12) < 2e-3
+    assert not np.array_equal(u[:16], P.uniform(16, 0.0, 1.0, seed=5, stream_id=1, step=0))
+    assert not np.array_equal(u[:16], P.uniform(16, 0.0, 1.0, seed=5, stream_id=0, step=1))
