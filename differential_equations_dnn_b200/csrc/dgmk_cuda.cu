@@ -677,6 +677,14 @@ struct CudaBackend : BackendTraitsAll {
     // every batch size.  g_tile == 2 forces the tile step.
     const int64_t tile_rows = P * (cls == DGMK_WS_HEAT ? 4 : 2);
     if (g_tile == 1 && c.n.Hp > 32 && B > 4096 && !(tile_rows >= 48 && B <= 16384)) return false;
+    // Small batches (the reference's own 32 .. 256 rows): a stage costs ~1000 cycles however few rows it has, so one
+    // full tile on one SM is the slowest possible plan -- spread the batch over the SMs in tiles of >= 4 points
+    // (64 rows: 16 CTAs of 4 points instead of 1 CTA of 64)
+    {
+      const int64_t per_cta = (B + sms - 1) / sms;
+      const int64_t Ps = per_cta < 4 ? 4 : per_cta;
+      if (Ps < P) P = Ps;
+    }
     // spread the points evenly over the tiles (same tile count, smaller ragged tail)
     const int64_t nt0 = (B + P - 1) / P;
     P = (B + nt0 - 1) / nt0;
@@ -702,7 +710,12 @@ struct CudaBackend : BackendTraitsAll {
       return (int64_t)pass_bytes(c.n, P, CS_V) + (int64_t)pass_bytes(c.n, P * J, CS_V) + (int64_t)rev_bytes(c.n, P * J, true) +
              (r4(P) * 2 + r4(P * J)) * 4;
     };
-    int64_t P = fa.B < 8 ? fa.B : 8, J = 0;
+    // points per block: at most 8, and few enough that a small batch still spreads over the SMs -- the reference's own
+    // step (32 points x 50 nodes) is 32 one-point blocks whose 50 node rows fit ONE sub-tile (no second node pass)
+    // instead of four 8-point blocks of three sub-tiles each
+    int64_t P = (fa.B + sms - 1) / sms, J = 0;
+    if (P > 8) P = 8;
+    if (P < 1) P = 1;
     for (int64_t q = 1; q <= fa.k; ++q) { if (need(P, q) <= budget) J = q; else break; }
     if (J < 1) return false;
     // measured (tools/tile_prof.py fredholm): 8-point blocks with ~17-node sub-tiles and the second node pass lose to
