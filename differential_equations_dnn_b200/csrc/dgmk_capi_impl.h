@@ -123,12 +123,13 @@ struct Api {
     if (!carve_ctx(cv, &c, 3 * ch)) return fail(DGMK_EWORKSPACE, "workspace too small");
     Pipeline<BK> P(bk, c);
     P.pack(theta);
-    P.zero_grads();
     HeatArgs ha; ha.x = x; ha.x0 = x0; ha.xbd1 = xbd1; ha.xbd2 = xbd2; ha.t_bd1 = t_bd1; ha.t_bd2 = t_bd2;
     ha.kappa = kappa; ha.inv = (float)(1.0 / (double)Bg);
     if constexpr (BK::kHasTile) {   // hidden sizes <= 64: the whole step in one persistent kernel (dgmk_tile.cuh)
-      if (bk.tile_step(c, DGMK_WS_HEAT, &ha, nullptr, B)) { P.unpack(grad, loss); return finish(bk); }
+      bk.set_unpack_target(grad, loss);
+      if (bk.tile_step(c, DGMK_WS_HEAT, &ha, nullptr, B)) { if (!bk.unpacked) P.unpack(grad, loss); return finish(bk); }
     }
+    P.zero_grads();
     const size_t mark = cv.off;
     for (int64_t p0 = 0; p0 < B; p0 += ch) {
       int64_t r = (B - p0 < ch) ? B - p0 : ch;
@@ -154,11 +155,12 @@ struct Api {
     if (!carve_ctx(cv, &c, ch)) return fail(DGMK_EWORKSPACE, "workspace too small");
     Pipeline<BK> P(bk, c);
     P.pack(theta);
-    P.zero_grads();
     OdeArgs oa; oa.t = t; oa.t0 = t0; oa.y_ic = y_ic; oa.inv = (float)(1.0 / (double)Bg); oa.fhn = fhn ? 1 : 0;
     if constexpr (BK::kHasTile) {
-      if (bk.tile_step(c, cls, nullptr, &oa, B)) { P.unpack(grad, loss); return finish(bk); }
+      bk.set_unpack_target(grad, loss);
+      if (bk.tile_step(c, cls, nullptr, &oa, B)) { if (!bk.unpacked) P.unpack(grad, loss); return finish(bk); }
     }
+    P.zero_grads();
     const size_t mark = cv.off;
     for (int64_t p0 = 0; p0 < B; p0 += ch) {
       int64_t r = (B - p0 < ch) ? B - p0 : ch;
@@ -183,13 +185,14 @@ struct Api {
     if (!carve_ctx(cv, &c, ch)) return fail(DGMK_EWORKSPACE, "workspace too small");
     Pipeline<BK> P(bk, c);
     P.pack(theta);
-    P.zero_grads();
     const float inv = (float)(1.0 / (double)Bg);
     const float dr = (float)(M_PI / (2.0 * k));
     FredArgs fa; fa.x = x; fa.nodes = nodes; fa.B = B; fa.k = k; fa.dr = dr; fa.inv = inv;
     if constexpr (BK::kHasTile) {   // hidden sizes <= 64: blocks of points, node sub-tiles in shared memory (dgmk_tile.cuh)
-      if (bk.tile_step_fredholm(c, fa)) { P.unpack(grad, loss); return finish(bk); }
+      bk.set_unpack_target(grad, loss);
+      if (bk.tile_step_fredholm(c, fa)) { if (!bk.unpacked) P.unpack(grad, loss); return finish(bk); }
     }
+    P.zero_grads();
     if (bk.fredholm_block_nodes() > 0) {   // (test harness) the sub-tiled body on the host
       const int64_t rb_ = bk.fredholm_block_points() < ch ? bk.fredholm_block_points() : ch;
       float* Ip = cv.take(rb_);

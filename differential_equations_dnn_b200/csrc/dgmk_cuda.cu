@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(EW_THREADS) ew4_kernel(const F f, int64_t n4) 
 // independent chains (loads in flight), the slices are combined in slice order.  (One thread per
 // output walking all partials -- the first version -- was latency-bound: 50-260 us per launch.)
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ part, int nparts, int64_t n,
-                                                               float* __restrict__ out, int cols, int64_t ldo) {
+                                                               float* __restrict__ out, int cols, int64_t ldo, bool overwrite) {
   const int64_t i = (int64_t)blockIdx.x * 32 + threadIdx.x;
   const int S = blockDim.y, sl = threadIdx.y;
   __shared__ double sm[32][33];
@@ -109,8 +109,43 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __re
     double t = 0.0;
     for (int k = 0; k < S; ++k) t += sm[k][threadIdx.x];
     const int64_t r = i / cols, c = i - r * cols;
-    out[r * ldo + c] += (float)t;
+    out[r * ldo + c] = overwrite ? (float)t : out[r * ldo + c] + (float)t;
   }
+}
+
+// Resident-tile step, small batches: second-stage reduction of the per-CTA partial gradients, scatter into the
+// caller's flat gradient (UnpackGradFn's mapping) and the loss in ONE launch.  Thread i < P owns parameter i and adds
+// its packed element over the nparts slots in FP64 (four chains, slot order); thread P does the loss.
+__global__ void __launch_bounds__(128) tile_unpack_kernel(const SegTable t, const float* __restrict__ part, int nparts, int64_t g_floats,
+                                                          int64_t g_acc, float* __restrict__ grad, float* __restrict__ loss, int64_t P) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > P) return;
+  int64_t off = -1;
+  if (i == P) off = g_acc;
+  else {
+    for (int s = 0; s < t.n; ++s) {
+      const Seg& g = t.s[s];
+      const int32_t k = (int32_t)i - g.theta_off;
+      if (k >= 0 && k < g.n) {
+        const int r = k / g.cols, c = k - r * g.cols;
+        if (g.a_off >= 0) off = g.a_off + (int64_t)r * g.a_rs + (int64_t)c * g.a_cs;
+        break;
+      }
+    }
+  }
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (off >= 0) {
+    const float* q = part + off;
+    int p = 0;
+    for (; p + 4 <= nparts; p += 4, q += 4 * g_floats) {
+      const float v0 = __ldg(q), v1 = __ldg(q + g_floats), v2 = __ldg(q + 2 * g_floats), v3 = __ldg(q + 3 * g_floats);
+      s0 += (double)v0; s1 += (double)v1; s2 += (double)v2; s3 += (double)v3;
+    }
+    for (; p < nparts; ++p, q += g_floats) s0 += (double)__ldg(q);
+  }
+  const float v = (float)((s0 + s1) + (s2 + s3));
+  if (i == P) { if (loss) *loss = v; }
+  else if (grad) grad[i] = v;
 }
 
 // DgmRev1Fn (hidden size 128) that also forms grad[U | b] of the Z, G and H gates -- the input-map
@@ -487,12 +522,12 @@ struct CudaBackend : BackendTraitsAll {
     lane_gemm(X, ldx, Wt, Hp, M, 1, e, 2.0);
   }
   // out[(i / cols) * ldo + i % cols] += sum_p part[p][i]   (cols = 0: out[i])
-  void reduce(const float* part, int nparts, int64_t n, float* out, int cols = 0, int64_t ldo = 0) {
+  void reduce(const float* part, int nparts, int64_t n, float* out, int cols = 0, int64_t ldo = 0, bool overwrite = false) {
     if (cols <= 0) { cols = (int)n; ldo = n; }
     // slices: enough to keep every chain short, few enough that small partial counts are not split to nothing
     const int S = nparts >= 512 ? 32 : (nparts >= 128 ? 16 : (nparts >= 16 ? 8 : 1));
     ProfScope ps(PC_OTHER, st, 0.0, 4.0 * nparts * (double)n);
-    reduce_partials_kernel<<<(unsigned)((n + 31) / 32), dim3(32, S), 0, st>>>(part, nparts, n, out, cols, ldo);
+    reduce_partials_kernel<<<(unsigned)((n + 31) / 32), dim3(32, S), 0, st>>>(part, nparts, n, out, cols, ldo, overwrite);
     post();
   }
   // out[N,Kd] += A^T S ; if E: outE[e * ldoE + n] += sum_m A[m,n] E[m,e]  (fused in the same pass)
@@ -632,9 +667,10 @@ struct CudaBackend : BackendTraitsAll {
                              ((size_t)prm.lp_floats + prm.coord_floats + prm.ip_floats) * 4 + prm.tile_bytes;
     // two CTAs per SM when the plan fits half an SM's shared memory (the kernels that allow it are compiled for it)
     const int64_t ctas = (int64_t)sms * ((prob != tk::PROB_HEAT && smem_need <= (size_t)tk::SMEM_HALF) ? 2 : 1);
-    const int64_t grid = ntiles < ctas ? ntiles : ctas;
+    int64_t grid = ntiles < ctas ? ntiles : ctas;
     const int64_t slots_avail = c.part_n / prm.g_floats;
-    if (slots_avail < grid) return false;
+    if (slots_avail < 1) return false;
+    if (grid > slots_avail) grid = slots_avail;   // (wide networks: fewer partial-gradient slots than SMs; CTAs walk more tiles)
     int64_t nseg = ((ntiles + grid - 1) / grid + g_tile_flush - 1) / g_tile_flush;
     if (nseg * grid > slots_avail) nseg = slots_avail / grid;
     prm.nslots_per_cta = (int32_t)nseg;
@@ -646,13 +682,35 @@ struct CudaBackend : BackendTraitsAll {
       note((cudaError_t)tk::launch(prob, prm, (int)grid, smem, st));
       ++g_launches;
     }
-    reduce(c.part, (int)(grid * nseg), prm.g_floats, c.Gp);
+    // The packed gradient IS the sum of the partials (the caller has not zeroed c.Gp).  Few partials (small batches,
+    // where every launch counts): sum, scatter into the caller's gradient and write the loss in one launch.
+    const int64_t nparts = grid * nseg;
+    unpacked = false;
+    if (nparts <= 64 && (out_grad || out_loss)) {
+      const int64_t np = num_params(c.n);
+      ProfScope ps(PC_OTHER, st, 0.0, 4.0 * nparts * (double)np);
+      tile_unpack_kernel<<<(unsigned)((np + 1 + 127) / 128), 128, 0, st>>>(c.grad, c.part, (int)nparts, prm.g_floats, c.pl.g_acc, out_grad, out_loss, np);
+      post();
+      unpacked = true;
+    } else {
+      reduce(c.part, (int)nparts, prm.g_floats, c.Gp, 0, 0, true);
+    }
     return !err;
   }
+  // where a tile step may deliver the flat gradient and the loss directly (set by the C API before tile_step*)
+  float* out_grad = nullptr; float* out_loss = nullptr; bool unpacked = false;
+  void set_unpack_target(float* grad, float* loss) { out_grad = grad; out_loss = loss; }
   static int64_t r4(int64_t v) { return (v + 3) / 4 * 4; }
   // Heat / ODE / FitzHugh-Nagumo.  false = shape not covered or the layer-wise path is faster (the caller runs it).
   bool tile_step(Ctx& c, int cls, const HeatArgs* ha, const OdeArgs* oa, int64_t B) {
     if (!g_tile || c.n.Hp > TILE_MAX_HP || B <= 0) return false;
+    // Hidden sizes above 64 (the headline 128) fit the tile step for small batches only (4 heat points per tile, weights
+    // and gradient accumulators through L2).  Measured at the reference's own 64 rows, DGM(2,1,128,3) under the CUDA-graph
+    // driver: 0.99 ms per iteration against 0.85 ms for the ~115 tcgen05 launches of the layer-wise path -- every GEMM
+    // stage waits on weight rows coming from L2 (ldg chains, two k-steps in flight).  So it is OFF by default and runs
+    // only when forced (dgmk_set_tile_engine(2): the parity tests cover it); staging weight panels through shared
+    // memory is the missing piece.
+    if (c.n.Hp > TILE_WIDE_HP && (g_tile != 2 || B > TILE_WIDE_ROWS)) return false;
     tk::TileParams prm;
     // per-point extras: loss contribution per loss row + the staged coordinates of the larger pass
     auto coord_fl = [&](int64_t P) { return r4((cls == DGMK_WS_HEAT ? 6 : 1) * P); };
@@ -702,7 +760,7 @@ struct CudaBackend : BackendTraitsAll {
   }
   // Fredholm: a tile is a block of P points with all their k nodes, the node rows taken J nodes at a time
   bool tile_step_fredholm(Ctx& c, const FredArgs& fa) {
-    if (!g_tile || c.n.Hp > TILE_MAX_HP || fa.B <= 0) return false;
+    if (!g_tile || c.n.Hp > TILE_WIDE_HP || fa.B <= 0) return false;
     tk::TileParams prm;
     const int64_t budget = tile_fixed(c, prm);
     prm.B = fa.B;

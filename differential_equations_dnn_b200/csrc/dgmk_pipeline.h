@@ -60,15 +60,19 @@ DGMK_HD int64_t rev_floats_per_row(const NetDims& n, int C) {
   return (2 * Hp + n.NG * Hp + (n.is_dgm() ? Hp : 0)) * C;
 }
 constexpr int64_t PART_FLOATS_MIN = 1 << 22;   // 16 MB: 2048 partials of a hidden-size-32 layer
-constexpr int TILE_MAX_HP = 64;          // hidden sizes the resident-tile step covers
+constexpr int TILE_MAX_HP = 128;         // hidden sizes the resident-tile step covers (above 64: small batches, and only when forced)
+constexpr int TILE_WIDE_HP = 64;         // ... above this only batches of <= TILE_WIDE_ROWS rows (the reference's own regime)
+constexpr int64_t TILE_WIDE_ROWS = 256;
 constexpr int64_t TILE_SLOTS = 320;      // per-CTA partial gradient slots it may ask for (>= 2 per SM)
+constexpr int64_t TILE_SLOTS_WIDE = 64;  // hidden sizes above TILE_WIDE_HP: one slot per 4-point tile of a 256-row batch
 inline int64_t part_floats(const NetDims& n) {
   // gemm_tn partials: >= 256 splits x [3Hp, Hp]; wcolsum partials: <= 512 blocks x 4 x 4Hp
   int64_t a = 256LL * (3 * n.Hp * n.Hp + 4 * 3 * n.Hp), b = 512LL * 4 * 4 * n.Hp;
   int64_t m = a > b ? a : b;
   if (n.Hp <= TILE_MAX_HP) {   // resident-tile step: one partial copy of the packed gradient per slot
     PackedLayout pl; make_packed_layout(n, &pl);
-    if (TILE_SLOTS * pl.g_total > m) m = TILE_SLOTS * pl.g_total;
+    const int64_t slots = n.Hp > TILE_WIDE_HP ? TILE_SLOTS_WIDE : TILE_SLOTS;
+    if (slots * pl.g_total > m) m = slots * pl.g_total;
   }
   return m > PART_FLOATS_MIN ? m : PART_FLOATS_MIN;
 }

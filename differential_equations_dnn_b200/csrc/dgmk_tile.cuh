@@ -173,14 +173,19 @@ __device__ __forceinline__ void colsum_finish(const ColsumJob& j, int tid0) {
     j.out[(j.ldo > 0 ? e * j.ldo : e * N) + c] += t;
   }
 }
+// (more columns than threads -- hidden size 128, three gates: one column block of NT per round; the loop lives in
+// this non-inlined function: in the callers' wrappers it cost the kernels ~400 bytes of spills)
 __device__ __noinline__ void wcolsum_impl(const float* __restrict__ Mat_, int ldm, int N, const float* __restrict__ Wt_, int M, float* out,
                                           int ldo, float* scratch_) {
-  ColsumJob j; j.Mat = Mat_; j.ldm = ldm; j.N = N; j.Wt = Wt_; j.M = M; j.out = out; j.ldo = ldo;
-  colsum_plan(j, scratch_, SCRATCH_FLOATS);
-  colsum_partial(j);
-  __syncthreads();
-  colsum_finish(j, 0);
-  __syncthreads();
+  for (int n0 = 0; n0 < N; n0 += NT) {
+    ColsumJob j; j.Mat = Mat_ + n0; j.ldm = ldm; j.N = N - n0 < NT ? N - n0 : NT; j.Wt = Wt_; j.M = M; j.out = out + n0;
+    j.ldo = ldo > 0 ? ldo : N;
+    colsum_plan(j, scratch_, SCRATCH_FLOATS);
+    colsum_partial(j);
+    __syncthreads();
+    colsum_finish(j, 0);
+    __syncthreads();
+  }
 }
 // The three column sums at the head of a reverse pass in ONE stage (two barriers instead of six): the pass's loss rows
 // (Lp == nullptr: none), grad W_out = UB^T S_L and grad b_out = UB^T E.  Same arithmetic and summation order as three

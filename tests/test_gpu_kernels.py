@@ -62,8 +62,25 @@ PROBS = ("heat", "ode", "fhn", "fredholm")
 CASES = [(p, n) for p in PROBS for n in golden_names(p + "_") if "driver" not in n]
 
 
+@pytest.fixture
+def tile_engine():
+    """dgmk_set_tile_engine for the duration of a test (0: layer-wise path only, 1: default dispatch, 2: the resident-tile
+    step wherever it fits)."""
+    from differential_equations_dnn_b200 import _cabi
+    lib = _cabi.load()
+
+    def set_engine(e):
+        lib.dgmk_set_tile_engine(e)
+    yield set_engine
+    lib.dgmk_set_tile_engine(1)
+
+
+@pytest.mark.parametrize("engine", [1, 0])
 @pytest.mark.parametrize("prob,name", CASES)
-def test_step_matches_reference(K, prob, name):
+def test_step_matches_reference(K, tile_engine, prob, name, engine):
+    """Every golden fixture through the default dispatch (hidden sizes <= 64: the resident-tile step) and through the
+    layer-wise path alone (FFMA2 tiles for the small networks; hidden size 128 runs the tcgen05 kernels either way)."""
+    tile_engine(engine)
     g = golden(name)
     loss, grad = run(K, prob, g)
     check(K, g, loss, grad)
@@ -73,9 +90,11 @@ def test_step_matches_reference(K, prob, name):
                                        ("fhn", "fhn_dgm_h64l2"), ("ode", "ode_mlp_relu_h32l1"),
                                        # hidden size 128: the fused tcgen05 kernels on 5-row chunks (tiles mostly padding)
                                        ("heat", "heat_dgm_h128l3"), ("fhn", "fhn_mlp_tanh_h128l3"), ("fhn", "fhn_dgm_h128l4")])
-def test_small_workspace_chunks(K, prob, name):
+def test_small_workspace_chunks(K, tile_engine, prob, name):
     from differential_equations_dnn_b200 import _cabi
     g = golden(name)
+    if "h128" in name:
+        tile_engine(0)   # the chunk loop of the layer-wise path is what this case is about
     cls = {"heat": _cabi.WS_HEAT, "fhn": _cabi.WS_FHN, "fredholm": _cabi.WS_FREDHOLM, "ode": _cabi.WS_ODE}[prob]
     k = g["T"].shape[0] if prob == "fredholm" else 0
     small = K.workspace_bytes(desc_of(g), cls, 5, k)
@@ -276,7 +295,8 @@ def test_engines_agree(K, kind, prob):
 # The resident-tile step (csrc/dgmk_tile.cuh: one persistent kernel per step for hidden sizes <= 64) against the
 # layer-wise path and the FP64 oracle: many tiles per CTA, ragged last tile, several FP32 accumulation segments,
 # weights / accumulators in shared memory (hidden size 32) and in L2 (hidden size 64, 3 layers), one and two CTAs per SM.
-@pytest.mark.parametrize("case", ["heat_dgm32", "heat_dgm64x3", "heat_mlp64", "ode_mlp32", "fhn_dgm32", "fredholm_dgmraw32", "fredholm_k70"])
+@pytest.mark.parametrize("case", ["heat_dgm32", "heat_dgm64x3", "heat_mlp64", "ode_mlp32", "fhn_dgm32", "fredholm_dgmraw32", "fredholm_k70",
+                                  "heat_dgm128x3", "heat_mlp128x3", "fhn_dgm128x4"])
 def test_tile_step_vs_layerwise_and_oracle(K, case):
     from differential_equations_dnn_b200 import _cabi, dgm_net, neural_networks
     from oracle import jets_np
@@ -284,9 +304,11 @@ def test_tile_step_vs_layerwise_and_oracle(K, case):
     torch.manual_seed(3)
     gen = torch.Generator().manual_seed(4)
     if case.startswith("heat"):
-        B = 5000 + 13
+        B = 203 if "128" in case else 5000 + 13   # hidden size 128: the tile step covers the small-batch regime only
         net = {"heat_dgm32": lambda: dgm_net.DGM(2, 1, 32, 1), "heat_dgm64x3": lambda: dgm_net.DGM(2, 1, 64, 3),
-               "heat_mlp64": lambda: neural_networks.MLP(2, 1, 50, 2, activation="sigmoid")}[case]().cuda()
+               "heat_mlp64": lambda: neural_networks.MLP(2, 1, 50, 2, activation="sigmoid"),
+               "heat_dgm128x3": lambda: dgm_net.DGM(2, 1, 128, 3),
+               "heat_mlp128x3": lambda: neural_networks.MLP(2, 1, 128, 3, activation="tanh")}[case]().cuda()
         x = torch.pi * torch.rand([B, 1], generator=gen); t = 3.0 * torch.rand([B, 1], generator=gen); z = torch.zeros(B, 1)
         host = [torch.cat([x, t], 1), torch.cat([x, z], 1), torch.cat([z, t], 1), torch.cat([z + torch.pi, t], 1), z, z.clone()]
         fn, ofn = K.heat_step, jets_np.heat_step
@@ -295,9 +317,8 @@ def test_tile_step_vs_layerwise_and_oracle(K, case):
         net = neural_networks.MLP(1, 1, 32, 1, activation="tanh").cuda()
         host = [1.01 * torch.rand([B, 1], generator=gen), torch.zeros(B, 1), 2.0 * torch.ones(B, 1)]
         fn, ofn = K.ode_step, jets_np.ode_step
-    elif case == "fhn_dgm32":
-        B = 9000 + 1
-        net = dgm_net.DGM(1, 2, 32, 2).cuda()
+    elif case.startswith("fhn_dgm"):
+        B, net = (100, dgm_net.DGM(1, 2, 128, 4).cuda()) if case == "fhn_dgm128x4" else (9000 + 1, dgm_net.DGM(1, 2, 32, 2).cuda())
         host = [30.01 * torch.rand([B, 1], generator=gen), torch.zeros(B, 1), torch.zeros(B, 2)]
         fn, ofn = K.fhn_step, jets_np.fhn_step
     else:
