@@ -666,7 +666,8 @@ struct CudaBackend : BackendTraitsAll {
     const size_t smem_need = (size_t)tk::SCRATCH_TOTAL_FLOATS * 4 + (prm.w_smem ? (size_t)prm.w_floats * 4 : 0) + (prm.g_smem ? (size_t)prm.g_floats * 4 : 0) +
                              ((size_t)prm.lp_floats + prm.coord_floats + prm.ip_floats) * 4 + prm.tile_bytes;
     // two CTAs per SM when the plan fits half an SM's shared memory (the kernels that allow it are compiled for it)
-    const int64_t ctas = (int64_t)sms * ((prob != tk::PROB_HEAT && smem_need <= (size_t)tk::SMEM_HALF) ? 2 : 1);
+    const bool two = prob != tk::PROB_HEAT && !(DGMK_TILE_DGM_ONE_CTA && c.n.is_dgm()) && smem_need <= (size_t)tk::SMEM_HALF;
+    const int64_t ctas = (int64_t)sms * (two ? 2 : 1);
     int64_t grid = ntiles < ctas ? ntiles : ctas;
     const int64_t slots_avail = c.part_n / prm.g_floats;
     if (slots_avail < 1) return false;
@@ -725,7 +726,7 @@ struct CudaBackend : BackendTraitsAll {
     // Two CTAs per SM hide each other's stage barriers (simple_ode MLP(1,1,32): 4.5e8 -> 5.0e8 rows/s) as long as a
     // half-SM tile still has >= 128 interior rows; smaller tiles lose more than the overlap gains (measured: heat
     // DGM(2,1,32,1) 15.7 -> 24.2 ms with 11-point tiles), and the heat kernels are compiled for one CTA per SM.
-    int64_t P = (cls == DGMK_WS_HEAT) ? 0 : plan(tk::SMEM_HALF);
+    int64_t P = (cls == DGMK_WS_HEAT || (DGMK_TILE_DGM_ONE_CTA && c.n.is_dgm())) ? 0 : plan(tk::SMEM_HALF);
     if (P * 2 < 128 && P < B) P = plan(tk::SMEM_MAX);
     prm.B = B;
     if (P < 2 && P < B) return false;

@@ -439,7 +439,7 @@ struct TileBackend {
 template <int PROB, class BK>
 // Register budget: the heat kernels (four-channel jets) want more than 128 registers and their tiles fill an SM's shared
 // memory anyway; the value-only / first-order kernels fit 128, so two CTAs can share an SM when the tile is small enough.
-__global__ void __launch_bounds__(NT, PROB == PROB_HEAT ? 1 : 2) tile_step_kernel(const __grid_constant__ TileParams prm) {
+__global__ void __launch_bounds__(NT, (PROB == PROB_HEAT || (DGMK_TILE_DGM_ONE_CTA && BK::dgm_on())) ? 1 : 2) tile_step_kernel(const __grid_constant__ TileParams prm) {
   float* sp = g_tile_smem;
   BK bk;
   bk.scratch = sp; sp += SCRATCH_TOTAL_FLOATS;

@@ -21,6 +21,11 @@ constexpr int SMEM_MAX = 232448;        // 227 KB opt-in limit per CTA on sm_100
 constexpr int SMEM_HALF = 115712;       // two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2
 constexpr int FLUSH_TILES = 256;        // tiles per FP32 accumulation segment
 
+// 1: the DGM kernels of the ODE / Fredholm classes get one CTA per SM and the whole register file (at two CTAs per SM they
+// spill ~500 B of stores / ~1700 B of loads under the 128-register cap); 0: two CTAs per SM like the MLP kernels
+#ifndef DGMK_TILE_DGM_ONE_CTA
+#define DGMK_TILE_DGM_ONE_CTA 1
+#endif
 enum { PROB_HEAT = 0, PROB_ODE = 1, PROB_FRED = 2 };   // ODE covers simple_ode and FitzHugh-Nagumo (OdeArgs::fhn)
 
 struct TileParams {

@@ -32,6 +32,9 @@ else:
     net = dgm_net.DGM(1, 2, H, L).cuda()
     a = [v.cuda() for v in (30.01 * torch.rand([B, 1], generator=gen), z, torch.zeros(B, 2))]
     fn = lambda: K.fhn_step(net.desc, net.flat_theta(), *a)
+if os.environ.get("TILE_ENGINE"):   # 0: layer-wise only, 2: the resident-tile step wherever it fits
+    from differential_equations_dnn_b200 import _cabi as _c
+    _c.load().dgmk_set_tile_engine(int(os.environ["TILE_ENGINE"]))
 for _ in range(2):
     out = fn()
 torch.cuda.synchronize()
