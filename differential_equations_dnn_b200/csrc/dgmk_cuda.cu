@@ -12,6 +12,7 @@
 #include "dgmk_wgrad_ws.cuh"
 #include "dgmk_lane_gemm.cuh"
 #include "dgmk_lane_epi.cuh"
+#include "dgmk_dgrad_res.cuh"
 #include "dgmk_tile_params.h"
 
 namespace dgmk {
@@ -25,6 +26,8 @@ static unsigned long long g_launches = 0;
 static bool g_use_tc = true;
 // fused units-on-lanes kernels (GEMM + element-wise stage in one launch) where the shape allows
 static bool g_fuse = true;
+// K = 3H data gradient on the weight-resident kernel (dgmk_dgrad_res.cuh); off: the round-1 streaming tile
+static bool g_dgrad_res = true;
 // resident-tile step (one persistent kernel per step) for hidden sizes <= 64 (dgmk_set_tile_engine)
 static int g_tile = 1;   // 0 off, 1 on where it wins (dispatch rule in tile_step), 2 forced on wherever it fits
 static long long* g_tile_prof = nullptr;   // dgmk_tile_profile: device buffer for CTA 0's stage timeline
@@ -324,14 +327,14 @@ struct CudaBackend : BackendTraitsAll {
   cudaStream_t st;
   const char* err;
   int sms;
-  bool use_tc, fuse;
+  bool use_tc, fuse, dgrad_res;
   int64_t hl_stride = 0;  // distance between the plain / tf32-hi / tf32-lo copies of the packed weights
   // design bytes (operands read + results written, each once) of the NEXT element-wise / reduction launch,
   // announced by the pipeline for the per-class traffic accounting of dgmk_profile
   double pending_bytes = 0.0;
   void note_bytes(double b) { pending_bytes = b; }
   double take_bytes() { double b = pending_bytes; pending_bytes = 0.0; return b; }
-  explicit CudaBackend(void* stream) : st((cudaStream_t)stream), err(nullptr), sms(148), use_tc(g_use_tc), fuse(g_fuse) {
+  explicit CudaBackend(void* stream) : st((cudaStream_t)stream), err(nullptr), sms(148), use_tc(g_use_tc), fuse(g_fuse), dgrad_res(g_dgrad_res) {
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) {
       int v = 0;
@@ -388,6 +391,23 @@ struct CudaBackend : BackendTraitsAll {
                     int64_t ldc, int64_t M, int N, int K, bool acc) {
     if (M <= 0) return;
     ProfScope ps(PC_STREAM_NN, st, 2.0 * M * N * K, 4.0 * M * (K + (acc ? 2.0 : 1.0) * N));
+    if (use_tc && dgrad_res && N == dg::BN && K % dg::KC == 0 && K > 128 && K <= dg::MAXCH * dg::KC) {
+      // weights resident in shared memory, rows through tensor memory (the K = 3H data gradient of a DGM layer)
+      if (first_use_on_device(3)) {
+        note(cudaFuncSetAttribute(dg::dgrad_res_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dg::SMEM_BYTES));
+        note(cudaFuncSetAttribute(dg::dgrad_res_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dg::SMEM_BYTES));
+      }
+      CUtensorMap tmA;
+      if (dg::make_a_map(&tmA, A, lda, M, K)) {
+        const int64_t ntiles = (M + dg::BM - 1) / dg::BM;
+        int64_t npairs = sms / 2 > 0 ? sms / 2 : 1;
+        if (npairs > ntiles) npairs = ntiles;
+        if (acc) dg::dgrad_res_kernel<true><<<(unsigned)(2 * npairs), dg::NT, dg::SMEM_BYTES, st>>>(tmA, Bt, ldbt, hl_stride, C, ldc, M, K);
+        else dg::dgrad_res_kernel<false><<<(unsigned)(2 * npairs), dg::NT, dg::SMEM_BYTES, st>>>(tmA, Bt, ldbt, hl_stride, C, ldc, M, K);
+        post();
+        return;
+      }
+    }
     if (use_tc && N % tc::BN == 0 && K % tc::KC == 0) {
       if (first_use_on_device(0)) {   // the opt-in is per function AND per device
         note(cudaFuncSetAttribute(tc::gemm_nn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
@@ -863,8 +883,11 @@ int dgmk_profile_read(int cls, double* ms, long long* launches, double* flops, d
   return 0;
 }
 // 0 = FP32 FFMA2 tiles only; 1 = tcgen05 3xTF32, fused GEMM + element-wise kernels where the shape
-// allows (default); 2 = tcgen05 3xTF32 streaming tiles + separate element-wise kernels
-void dgmk_set_gemm_engine(int engine) { dgmk::g_use_tc = engine != 0; dgmk::g_fuse = engine == 1; }
+// allows (default); 2 = tcgen05 3xTF32 streaming tiles + separate element-wise kernels; 3 = like 1, but the K = 3H data
+// gradient on the round-1 streaming tile instead of the weight-resident kernel (A/B measurements)
+void dgmk_set_gemm_engine(int engine) {
+  dgmk::g_use_tc = engine != 0; dgmk::g_fuse = engine == 1 || engine == 3; dgmk::g_dgrad_res = engine == 1;
+}
 // 1 (default) = hidden sizes <= 64 run the resident-tile step (one persistent kernel per step, dgmk_tile.cuh);
 // 0 = the layer-wise path for every hidden size (A/B measurements, tests of the layer-wise path at small sizes);
 // 2 = the resident-tile step wherever a tile fits, whatever the dispatch rule says

@@ -153,7 +153,8 @@ unsigned long long dgmk_launch_count(void); /* kernels launched by this library 
 int dgmk_ffma_probe(const float* in, float* out, int blocks, int iters, void* stream);
 /* 0: FP32 FFMA2 tiles only; 1 (default): tcgen05 3xTF32, fused GEMM + element-wise kernels and the
  * warp-specialised weight gradient where the shape allows; 2: tcgen05 3xTF32 streaming tiles +
- * separate element-wise kernels */
+ * separate element-wise kernels; 3: like 1 with the K = 3H data gradient of a DGM layer on the
+ * streaming tile instead of the weight-resident kernel (dgmk_dgrad_res.cuh) */
 void dgmk_set_gemm_engine(int engine);
 /* 1 (default): hidden sizes <= 64 run the resident-tile step -- the whole step (forward jets, loss, reverse,
  * per-CTA gradient accumulation) in ONE persistent kernel with the activation stash and the packed weights in

@@ -54,6 +54,8 @@ def test_sass_is_sm100a(cabi):
             assert c["UTCHMMA"] >= 12 and c["LDTM"] > 0 and c["UBLKCP"] + c["LDG"] > 0, name
         if "lane_gemm_kernel" in name:
             assert c["STTM"] > 0 and c["UBLKCP"] > 0, name     # weights resident in tensor memory, rows by bulk copy
+        if "dgrad_res_kernel" in name:   # rows by TMA tensor copies into tensor memory, weights resident in shared memory
+            assert c["UTCHMMA"] >= 12 and c["UTMALDG"] > 0 and c["STTM"] > 0 and c["LDTM"] > 0, name
         if "small_step_kernel" in name:
             assert c["UBLKCP"] > 0 and c["FFMA"] > 100, name   # weights staged by the bulk-copy engine, FP32 FMA pipe
 

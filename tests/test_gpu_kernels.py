@@ -400,3 +400,62 @@ def test_philox_heat_kernel_is_bit_exact(K, B):
         assert np.array_equal(bufs[0].cpu().numpy(), PH.heat(B, np.pi, 3.0, np.pi, 99, 17 + it)[0])
     with pytest.raises(K.DgmkError):
         K.sample_uniform(torch.zeros(4), 0.0, 1.0, 0)   # host tensor: no CPU path
+
+
+def _dgrad_probe(lib, engine, A, Bt3, M, K, ld):
+    import ctypes as C
+    lib.dgmk_gemm_tc_probe.restype = C.c_int
+    lib.dgmk_gemm_tc_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_void_p]
+    lib.dgmk_set_gemm_engine(engine)
+    try:
+        out = torch.full((M, ld), 7.0, device="cuda")
+        rc = lib.dgmk_gemm_tc_probe(A.data_ptr(), Bt3.data_ptr(), out.data_ptr(), M, 128, K, ld, None)
+        torch.cuda.synchronize()
+    finally:
+        lib.dgmk_set_gemm_engine(1)
+    assert rc == 0, lib.dgmk_last_error()
+    assert bool((out[:, 128:] == 7.0).all()), "wrote outside the result block"
+    return out[:, :128]
+
+
+@pytest.mark.parametrize("M,K", [(1, 384), (257, 384), (40000, 384), (5000, 256), (333, 160)])
+def test_dgrad_resident_kernel_vs_fp64(M, K):
+    """The weight-resident K = 3H data-gradient kernel (csrc/dgmk_dgrad_res.cuh; the reverse of dgm_net.py:53-68's
+    [Z | G | R] maps) against an FP64 product and the round-1 streaming tile: ragged row counts, several tiles per CTA."""
+    from differential_equations_dnn_b200 import _cabi
+    lib = _cabi.load()
+    ld = 512
+    g = torch.Generator(device="cuda").manual_seed(M)
+    A = torch.randn(M, ld, device="cuda", generator=g)
+    w = (torch.rand(128, K, device="cuda", generator=g) - 0.5) * 0.3
+    hi = ((w.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    Bt3 = torch.cat([w.reshape(-1), hi.reshape(-1), (w - hi).reshape(-1)]).contiguous()
+    ref = A[:, :K].double() @ w.double().t()
+    for engine in (1, 3):
+        out = _dgrad_probe(lib, engine, A, Bt3, M, K, ld)
+        err = float((out.double() - ref).norm() / ref.norm())
+        assert err < 5e-7, (engine, err)
+
+
+def test_dgrad_resident_kernel_ring_hand_over_is_exact():
+    """Every product is exact here (one-hot weights; A[r, k] encodes tile, chunk and position in the chunk), so a result
+    names the tile / chunk / column it was read from: guards the hand-over of the raw ring (a stage released while its
+    last shared-memory loads were still queued showed up as values of chunk g + 2, only in the MMA-bound steady state,
+    i.e. from the second tile of a CTA on)."""
+    from differential_equations_dnn_b200 import _cabi
+    lib = _cabi.load()
+    K, ld = 384, 512
+    M = 74 * 128 * 4
+    r = torch.arange(M, device="cuda")
+    kk = torch.arange(K, device="cuda")
+    w = torch.zeros(128, K, device="cuda")
+    for n in range(128):
+        w[n, 32 * (n % 12) + (3 * (n // 12) + n) % 32] = 1.0
+    Bt3 = torch.cat([w.reshape(-1), w.reshape(-1), torch.zeros_like(w).reshape(-1)]).contiguous()
+    for first in (r // 128, r % 128):
+        A = torch.zeros(M, ld, device="cuda")
+        A[:, :K] = first.float()[:, None] + 512.0 * (kk // 32).float()[None, :] + (kk % 32).float()[None, :] / 32
+        ref = (A[:, :K].double() @ w.double().t()).float()
+        for rep in range(3):
+            out = _dgrad_probe(lib, 1, A, Bt3, M, K, ld)
+            assert int((out != ref).sum()) == 0
