@@ -391,7 +391,7 @@ struct CudaBackend : BackendTraitsAll {
                     int64_t ldc, int64_t M, int N, int K, bool acc) {
     if (M <= 0) return;
     ProfScope ps(PC_STREAM_NN, st, 2.0 * M * N * K, 4.0 * M * (K + (acc ? 2.0 : 1.0) * N));
-    if (use_tc && dgrad_res && N == dg::BN && K % dg::KC == 0 && K > 128 && K <= dg::MAXCH * dg::KC) {
+    if (use_tc && dgrad_res && N == dg::BN && K % (2 * dg::KC) == 0 && K > 128 && K <= dg::MAXCH * dg::KC) {
       // weights resident in shared memory, rows through tensor memory (the K = 3H data gradient of a DGM layer)
       if (first_use_on_device(3)) {
         note(cudaFuncSetAttribute(dg::dgrad_res_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dg::SMEM_BYTES));

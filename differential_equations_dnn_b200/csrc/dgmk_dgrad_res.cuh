@@ -69,14 +69,14 @@ constexpr int MAXCH = 12;          // K <= 384
 constexpr int B_LBO = 1024, B_SBO = 128;     // weight operand [64 x 32]: 8 core-matrix columns of 8 row groups
 constexpr int B_OPER = 8 * B_LBO;
 constexpr int B_CHUNK = 2 * B_OPER;          // hi | lo
-constexpr int NSLOT = 4;
+constexpr int NSLOT = 2;            // round slots: a round = two chunks (hops between the roles cost more than the work of one chunk)
 constexpr int W_DRAIN = 8, W_ISSUE = 16;
 constexpr int NT = 20 * 32;
 constexpr int RAW_OFF = MAXCH * B_CHUNK;     // raw ring: 2 stages of one chunk, [128 rows x 128 B], XOR-swizzled 16-byte pieces
 constexpr int RAW_BYTES = BM * KC * 4;
 constexpr int BAR_OFF = RAW_OFF + 2 * RAW_BYTES;
 constexpr int SMEM_BYTES = BAR_OFF + 256;
-constexpr int TM_A = 0, TM_D = NSLOT * 64;
+constexpr int TM_A = 0, TM_D = NSLOT * 128;   // per round slot: 2 x (32 hi | 32 lo) columns of A, 2 x 64 accumulator columns
 constexpr int TMEM_COLS = 512;
 // launch allocation 640 x 96 = 61440 >= 256 x 96 + 256 x 120 + 128 x 40 = 60416
 constexpr int REGS_LOAD = 96, REGS_DRAIN = 120, REGS_ISSUE = 40;
@@ -119,7 +119,7 @@ inline bool make_a_map(CUtensorMap* tm, const float* A, int64_t lda, int64_t M, 
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// grid = 2 * npairs (CTA b: pair b / 2, output units 64 (b % 2) ..).  K % 32 == 0, 32 <= K <= 384, lda / ldb / ldc % 4 == 0.
+// grid = 2 * npairs (CTA b: pair b / 2, output units 64 (b % 2) ..).  K % 64 == 0, 64 <= K <= 384, lda / ldb / ldc % 4 == 0.
 template <bool ACCUM>
 __global__ void __launch_bounds__(NT, 1) dgrad_res_kernel(const __grid_constant__ CUtensorMap tmA, const float* __restrict__ Bt,
                                                           int64_t ldb, int64_t hl_stride, float* __restrict__ C, int64_t ldc,
@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(NT, 1) dgrad_res_kernel(const __grid_constant_
   const int64_t ntiles = (M + BM - 1) / BM;
   const uint32_t my_tiles = (pair < ntiles) ? (uint32_t)((ntiles - pair + npairs - 1) / npairs) : 0u;
   const uint32_t G = my_tiles * (uint32_t)nch;   // chunks this CTA walks (32-bit: the host launches slabs of < 2^31 rows)
+  const uint32_t NR = G >> 1;                    // rounds of two chunks (nch is even)
 
   if (warp == W_ISSUE) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tc::smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
@@ -144,8 +145,8 @@ __global__ void __launch_bounds__(NT, 1) dgrad_res_kernel(const __grid_constant_
   }
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) {
-      tc::mbar_init(A_FULL + 8 * s, 128);    // every loader thread of one warpgroup (its tcgen05.st has completed)
-      tc::mbar_init(A_EMPTY + 8 * s, 256);   // every drain thread, once it has seen the chunk's MMAs complete (D_FULL)
+      tc::mbar_init(A_FULL + 8 * s, 256);    // every transformer thread (its tcgen05.st has completed)
+      tc::mbar_init(A_EMPTY + 8 * s, 256);   // every drain thread, once it has seen the round's MMAs complete (D_FULL)
       tc::mbar_init(D_FULL + 8 * s, 1);      // tcgen05.commit
       tc::mbar_init(D_EMPTY + 8 * s, 256);   // every drain thread
     }
@@ -177,20 +178,20 @@ __global__ void __launch_bounds__(NT, 1) dgrad_res_kernel(const __grid_constant_
   if (warp < W_DRAIN) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS_LOAD));
     // ================================ transformers: raw ring -> hi / lo -> TMEM =====================================
-    // thread = row of the tile = TMEM lane (tcgen05.st 32x32b); warpgroup w takes the chunks g = w (mod 2), which the
-    // copy warps put into ring stage w.  The stage is handed back as soon as the row sits in registers.
+    // thread = row of the tile = TMEM lane (tcgen05.st 32x32b); warpgroup w takes chunk 2 R + w of round R, which the
+    // copy thread put into ring stage w, and writes half w of the round's A slot.
     const int wg = warp >> 2, quarter = warp & 3;
-    const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16) + TM_A;
+    const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16) + TM_A + wg * 64;
     const char* prow = smem + RAW_OFF + wg * RAW_BYTES + (quarter * 32 + lane) * 128;
     const int sw = (int)((tc::smem_u32(prow) >> 7) & 7);   // = lane & 7 for a 1024-byte aligned ring
     DG_DECL;
     DG_T(tl0);
 #pragma unroll 1
-    for (uint32_t g = (uint32_t)wg; g < G; g += 2) {
-      const int slot = (int)(g & (NSLOT - 1));
-      const uint32_t u = g >> 2, k = g >> 1;
+    for (uint32_t R = 0; R < NR; ++R) {
+      const int rs = (int)(R & 1);
+      const uint32_t ur = R >> 1;
       DG_T(t0);
-      tc::mbar_wait(RAW_FULL + 8 * wg, k & 1);
+      tc::mbar_wait(RAW_FULL + 8 * wg, R & 1);
       DG_ADD(0, t0);
       DG_T(t1);
       float4 x[8];
@@ -210,11 +211,11 @@ __global__ void __launch_bounds__(NT, 1) dgrad_res_kernel(const __grid_constant_
       lg::mbar_arrive(RAW_EMPTY + 8 * wg);
       DG_ADD(1, t1);
       DG_T(t2);
-      tc::mbar_wait(A_EMPTY + 8 * slot, (u & 1) ^ 1);   // the MMAs of chunk g - 4 have read this slot
+      tc::mbar_wait(A_EMPTY + 8 * rs, (ur & 1) ^ 1);   // the MMAs of round R - 2 have read this slot
       DG_ADD(2, t2);
       DG_T(t3);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const uint32_t ta = tlane + slot * 64;
+      const uint32_t ta = tlane + rs * 128;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 xa = x[2 * q], xb = x[2 * q + 1], ha = h[2 * q], hb = h[2 * q + 1];
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(NT, 1) dgrad_res_kernel(const __grid_constant_
       }
       asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-      lg::mbar_arrive(A_FULL + 8 * slot);
+      lg::mbar_arrive(A_FULL + 8 * rs);
       DG_ADD(3, t3);
     }
     DG_ADD(4, tl0);
@@ -237,26 +238,27 @@ __global__ void __launch_bounds__(NT, 1) dgrad_res_kernel(const __grid_constant_
     const int quarter = warp & 3, part = (warp - W_DRAIN) >> 2;
     const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + TM_D + part * 32;
     const int col0 = half * BNH + part * 32 + 2 * (lane & 3);
+    const int rpt = nch >> 1;   // rounds per tile
     float acc[32];
-    int c = 0;
+    int rt = 0;                 // round of the tile
     uint32_t ti = 0;
     DG_DECL;
     DG_T(td0);
 #pragma unroll 1
-    for (uint32_t g = 0; g < G; ++g) {
-      const int slot = (int)(g & (NSLOT - 1));
-      const uint32_t u = (uint32_t)(g >> 2);
-      if (ACCUM && c == (nch > 3 ? nch - 3 : 0)) {   // this warp's part of the C tile into L2 before the read-modify-write
+    for (uint32_t R = 0; R < NR; ++R) {
+      const int rs = (int)(R & 1);
+      const uint32_t ur = R >> 1;
+      const int64_t row0 = (pair + (int64_t)ti * npairs) * BM + quarter * 32 + (lane >> 2);
+      float* cb = C + row0 * ldc + col0;
+      if (ACCUM && rt == (rpt > 1 ? rpt - 2 : 0)) {   // this warp's part of the C tile into L2 before the read-modify-write
         const int64_t row = (pair + (int64_t)ti * npairs) * BM + quarter * 32 + lane;
         if (row < M) prefetch_l2(C + row * ldc + half * BNH + part * 32);
       }
-      // last chunk of the tile: the thread's 16 pieces of the old C go out BEFORE the wait, so that their latency hides
-      // behind the chunk's MMAs (issued after the tile they cost ~3000 cycles, during which the accumulator ring filled
+      // last round of the tile: the thread's 16 pieces of the old C go out BEFORE the wait, so that their latency hides
+      // behind the round's MMAs (issued after the tile they cost ~3000 cycles, during which the accumulator ring filled
       // up and the tensor pipe stopped)
       float2 old[16];
-      const bool last = (c == nch - 1) && !DG_DBG(4);
-      const int64_t row0 = (pair + (int64_t)ti * npairs) * BM + quarter * 32 + (lane >> 2);
-      float* cb = C + row0 * ldc + col0;
+      const bool last = (rt == rpt - 1) && !DG_DBG(4);
       if (ACCUM && last) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) {   // k = 8 hb + 2 v2 + v1
@@ -265,23 +267,28 @@ __global__ void __launch_bounds__(NT, 1) dgrad_res_kernel(const __grid_constant_
         }
       }
       DG_T(t0);
-      tc::mbar_wait(D_FULL + 8 * slot, u & 1);
+      tc::mbar_wait(D_FULL + 8 * rs, ur & 1);
       DG_ADD(0, t0);
       DG_T(t1);
-      lg::mbar_arrive(A_EMPTY + 8 * slot);   // the chunk's MMAs are complete: its A columns can take chunk g + 4
+      lg::mbar_arrive(A_EMPTY + 8 * rs);   // the round's MMAs are complete: its A columns can take round R + 2
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      uint32_t v0[16], v1[16];
-      tmem_ld16x256b_x4(tbase + slot * 64, v0);
-      tmem_ld16x256b_x4(tbase + ((uint32_t)16 << 16) + slot * 64, v1);
-      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-      lg::mbar_arrive(D_EMPTY + 8 * slot);   // these columns can take chunk g + 4
-      if (c == 0) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { acc[j] = __uint_as_float(v0[j]); acc[16 + j] = __uint_as_float(v1[j]); }
-      } else {
+      for (int j = 0; j < 2; ++j) {   // the two chunk results of the round
+        uint32_t v0[16], v1[16];
+        tmem_ld16x256b_x4(tbase + rs * 128 + j * 64, v0);
+        tmem_ld16x256b_x4(tbase + ((uint32_t)16 << 16) + rs * 128 + j * 64, v1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        if (j == 1) {
+          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+          lg::mbar_arrive(D_EMPTY + 8 * rs);   // these columns can take round R + 2
+        }
+        if (j == 0 && rt == 0) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { acc[j] += __uint_as_float(v0[j]); acc[16 + j] += __uint_as_float(v1[j]); }
+          for (int i = 0; i < 16; ++i) { acc[i] = __uint_as_float(v0[i]); acc[16 + i] = __uint_as_float(v1[i]); }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { acc[i] += __uint_as_float(v0[i]); acc[16 + i] += __uint_as_float(v1[i]); }
+        }
       }
       DG_ADD(1, t1);
       if (last) {   // tile complete
@@ -297,8 +304,7 @@ __global__ void __launch_bounds__(NT, 1) dgrad_res_kernel(const __grid_constant_
         }
         DG_ADD(2, t2);
       }
-      ++c;
-      if (c == nch) { c = 0; ++ti; }
+      if (++rt == rpt) { rt = 0; ++ti; }
     }
     DG_ADD(3, td0);
     if (warp == W_DRAIN) { DG_OUT(8); }
@@ -306,48 +312,51 @@ __global__ void __launch_bounds__(NT, 1) dgrad_res_kernel(const __grid_constant_
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS_ISSUE));
     if (warp == W_ISSUE || warp == W_ISSUE + 2) {
       // ================================ MMA issuers ===================================================================
-      // Two warps on alternate chunks: between the last MMA of a chunk and the first of its next one an issuer spends
-      // ~300 cycles on barriers, descriptors and the commit, longer than the tensor pipe's queue lasts; with a second
-      // issuer the other chunk's MMAs run meanwhile (chunks are independent: own A slot, own accumulator columns).
-      const int iw = (warp - W_ISSUE) >> 1, istep = 2;
+      // Two warps on alternate rounds (issuer i owns round slot i): between the last MMA of a round and the first of
+      // its next one an issuer spends ~300 cycles on barriers, descriptors and the commit, longer than the tensor
+      // pipe's queue lasts; with a second issuer the other round's MMAs run meanwhile (rounds are independent: own A
+      // slot, own accumulator columns).
+      const int iw = (warp - W_ISSUE) >> 1;
       const uint32_t sb = tc::smem_u32(smem);
-      int c = iw % nch;
+      int c = (2 * iw) % nch;
       DG_DECL;
       DG_T(ti0);
 #pragma unroll 1
-      for (uint32_t g = (uint32_t)iw; g < G; g += istep) {
-        const int slot = (int)(g & (NSLOT - 1));
-        const uint32_t u = (uint32_t)(g >> 2);
+      for (uint32_t R = (uint32_t)iw; R < NR; R += 2) {
+        const uint32_t ur = R >> 1;
         DG_T(t0);
-        tc::mbar_wait(D_EMPTY + 8 * slot, (u & 1) ^ 1);   // accumulator columns drained by all 8 warps
+        tc::mbar_wait(D_EMPTY + 8 * iw, (ur & 1) ^ 1);   // accumulator columns drained by all 8 warps
         DG_ADD(0, t0);
         DG_T(t1);
-        tc::mbar_wait(A_FULL + 8 * slot, u & 1);
+        tc::mbar_wait(A_FULL + 8 * iw, ur & 1);
         DG_ADD(1, t1);
         DG_T(t2);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const uint64_t dBh = lg::make_desc(sb + c * B_CHUNK, B_LBO), dBl = lg::make_desc(sb + c * B_CHUNK + B_OPER, B_LBO);
-        const uint32_t ah = tmem + TM_A + slot * 64, al = ah + 32;
-        const uint32_t d = tmem + TM_D + slot * 64;
-        if (lg::elect_one()) {
-          if (!DG_DBG(1)) {
 #pragma unroll
-          for (int ks = 0; ks < KC / 8; ++ks) {   // small terms first
-            const uint64_t adv = (uint64_t)((ks * 2 * B_LBO) >> 4);
-            lg::mma_ts(d, al + ks * 8, dBh + adv, ks > 0 ? 1u : 0u);
-            lg::mma_ts(d, ah + ks * 8, dBl + adv, 1u);
-          }
+        for (int j = 0; j < 2; ++j) {
+          const uint64_t dBh = lg::make_desc(sb + (c + j) * B_CHUNK, B_LBO), dBl = lg::make_desc(sb + (c + j) * B_CHUNK + B_OPER, B_LBO);
+          const uint32_t ah = tmem + TM_A + iw * 128 + j * 64, al = ah + 32;
+          const uint32_t d = tmem + TM_D + iw * 128 + j * 64;
+          if (lg::elect_one()) {
+            if (!DG_DBG(1)) {
 #pragma unroll
-          for (int ks = 0; ks < KC / 8; ++ks) {
-            const uint64_t adv = (uint64_t)((ks * 2 * B_LBO) >> 4);
-            lg::mma_ts(d, ah + ks * 8, dBh + adv, 1u);
+              for (int ks = 0; ks < KC / 8; ++ks) {   // small terms first
+                const uint64_t adv = (uint64_t)((ks * 2 * B_LBO) >> 4);
+                lg::mma_ts(d, al + ks * 8, dBh + adv, ks > 0 ? 1u : 0u);
+                lg::mma_ts(d, ah + ks * 8, dBl + adv, 1u);
+              }
+#pragma unroll
+              for (int ks = 0; ks < KC / 8; ++ks) {
+                const uint64_t adv = (uint64_t)((ks * 2 * B_LBO) >> 4);
+                lg::mma_ts(d, ah + ks * 8, dBh + adv, 1u);
+              }
+            }
+            if (j == 1) tc::mma_commit(D_FULL + 8 * iw);   // one commit per round (a commit costs the issuer ~100 cycles)
           }
-          }
-          tc::mma_commit(D_FULL + 8 * slot);   // (one commit per chunk: a second one costs the issuer ~100 cycles)
+          __syncwarp();
         }
-        __syncwarp();
         DG_ADD(2, t2);
-        c = (c + istep) % nch;
+        c = (c + 4) % nch;
       }
       DG_ADD(3, ti0);
       if (warp == W_ISSUE) { DG_OUT(16); }
