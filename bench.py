@@ -489,7 +489,7 @@ def main():
     prof = {}
     names = {0: "wg::wgrad_ws_kernel (weight gradient: warp-specialised tcgen05 kind::tf32, A^T in tensor memory, 3xTF32)",
              1: "lg::lane_gemm_kernel (fused GEMM + jet stage: weights in tensor memory, warp-specialised, 3xTF32)",
-             2: "tc::gemm_nn_tc_kernel (streaming tcgen05 tile: K = 3H data gradient; FFMA2 tiles for H % 128 != 0)",
+             2: "dg::dgrad_res_kernel (K = 3H data gradient: weights resident in shared memory, rows by TMA through tensor memory, 3xTF32; FFMA2 tiles for H % 128 != 0)",
              3: "ew_kernel<...> / rev1_ev_kernel (stand-alone element-wise jet stages, loss, pack, Adam)",
              4: "wcolsum / rowdot / reduce_partials (output layer, column sums, second-stage reductions)",
              5: "tk::tile_step_kernel (hidden size <= 64: resident-tile step -- one persistent kernel, a tile of points through "

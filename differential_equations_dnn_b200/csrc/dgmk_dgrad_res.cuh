@@ -24,16 +24,19 @@
 // Arithmetic is the one of dgmk_gemm_tc.cuh: per K chunk lo*hi + hi*lo then hi*hi from zero in TMEM (12 MMAs, M = 128,
 // N = 64, K = 8), the chunk results added in round-to-nearest FP32 registers (the tensor core adds with truncation).
 //
-// 20 warps, decoupled by mbarriers (rings of 4 in TMEM: 4 x 64 columns of A (hi | lo), 4 x 64 accumulator columns):
+// 20 warps, decoupled by mbarriers.  The unit of hand-over between the roles is a ROUND of two chunks (a hop through a
+// barrier costs every role a few hundred cycles -- more than the work of one chunk; with one hop per chunk the bare
+// pipeline, no MMAs, ran at ~780 cycles per chunk against 640 cycles of MMAs).  TMEM: 2 round slots x [2 x (32 hi | 32 lo)
+// columns of A] + 2 round slots x [2 x 64 accumulator columns].
 //   warp 17      copy: one TMA tensor copy (cp.async.bulk.tensor.2d, 128-byte swizzle) of chunk g into raw-ring stage
 //                g % 2 (all the shared memory the weights leave: 2 x 16 KB), L2 prefetch of the chunk 8 ahead
-//   warps 0-7    transformers: warpgroup 0 takes the even chunks, warpgroup 1 the odd ones (thread = row = TMEM lane)
-//   warps 8-15   drain: warp w reads lanes 32 (w % 4).., columns 32 ((w - 8) / 4).. of each chunk result as soon as it is
-//                complete and hands the columns back; the 16x256b fragment shape of tcgen05.ld puts 32 contiguous bytes
-//                of a row of C into four neighbouring threads, so the read-modify-write of C after the last chunk runs
-//                on whole sectors without a transposition (no shared memory left for one: weights + raw ring)
-//   warps 16, 18 MMA issuers on alternate chunks (one elected lane each, warp-uniform control flow); warp 19 only hands its
-//                registers over
+//   warps 0-7    transformers: warpgroup w takes chunk 2 R + w of round R (thread = row = TMEM lane)
+//   warps 8-15   drain: warp w reads lanes 32 (w % 4).., columns 32 ((w - 8) / 4).. of the round's two chunk results and
+//                hands the columns back; the 16x256b fragment shape of tcgen05.ld puts 32 contiguous bytes of a row of C
+//                into four neighbouring threads, so the read-modify-write of C after the last round runs on whole
+//                sectors without a transposition (no shared memory left for one: weights + raw ring)
+//   warps 16, 18 MMA issuers on alternate rounds (one elected lane each, warp-uniform control flow); warp 19 only hands
+//                its registers over
 #pragma once
 #include <cuda.h>   // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 #include "dgmk_gemm_tc.cuh"

@@ -21,6 +21,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:tile_step -c 1 -o $OUT/r02_tile_ode_final python tools/tile_prof.py ode 32 1 1048576 1 > $OUT/ncu_tile_ode.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:tile_step -c 1 -o $OUT/r02_tile_heat32_final python tools/tile_prof.py heat 32 1 262144 1 > $OUT/ncu_tile_heat.log 2>&1
 ncu --set full --clock-control none -k regex:lane_gemm -s 372 -c 6 -o $OUT/r02_lane_gemm_final python tools/quick_bench.py > $OUT/ncu_lane.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:dgrad_res -s 66 -c 2 -o $OUT/r02_dgrad_res_final python tools/quick_bench.py > $OUT/ncu_dgrad.log 2>&1
 for f in heat ode fhn fredholm fhn_dgm heat_h32l1 heat_mlp; do python - <<PY
 import json
 try:
