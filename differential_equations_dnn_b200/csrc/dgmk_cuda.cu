@@ -4,6 +4,7 @@
 // This is the only implementation the package loads: there is no CPU path.
 #include <cuda_runtime.h>
 #include <atomic>
+#include <cstdlib>
 #include <vector>
 #include "dgmk_capi_impl.h"
 #include "dgmk_gemm.cuh"
@@ -450,8 +451,11 @@ struct CudaBackend : BackendTraitsAll {
     int64_t grid, c0 = 0, c1 = 0;
     if (ngates == 1) {
       grid = ntiles < sms ? ntiles : sms;
-    } else {   // three gates; the third (R: also forms s*R) costs ~15 % more per tile
-      c0 = (int64_t)(sms / 3.15);
+    } else {   // three gates; the third (R: also forms s*R) costs ~40 % more epilogue time per tile
+      // (measured with two MMA issuers, where the R gate's epilogue is what its CTAs wait for: 3.15 / 3.3 / 3.45 / 3.6 ->
+      // lane class 48.8 / 46.5 / 47.6 / 48.1 ms per 2^20 heat rows; DGMK_GATE_SPLIT overrides for such sweeps)
+      static const double split = [] { const char* e = getenv("DGMK_GATE_SPLIT"); double v = e ? atof(e) : 0.0; return v > 3.0 ? v : 3.3; }();
+      c0 = (int64_t)(sms / split);
       if (c0 > ntiles) c0 = ntiles;
       if (c0 < 1) c0 = 1;
       c1 = c0;

@@ -30,8 +30,10 @@
 //   warp 0       bulk-copy producer: cp.async.bulk (TMA engine; rows are contiguous, no tensor map
 //                needed) of the next [64 x 128] FP32 row tile into a 3-deep raw ring
 //   warps 4-7    transform: raw tile -> tf32 hi / lo -> UMMA canonical K-major operand tile (2-deep)
-//   warp 1       MMA issuer: per K chunk 12 tcgen05.mma (A = weights in TMEM, B = rows in smem,
-//                M=128, N=64, K=8) -> tcgen05.commit per chunk; frees the operand tile at the end
+//   warps 1-2    MMA issuers on alternate K chunks (round 2: the plain GEMM 0.37 -> 0.28 ms per 524 288 rows x 384
+//                units; the fused stages are epilogue- / HBM-bound and gain little): per K chunk 12 tcgen05.mma
+//                (A = weights in TMEM, B = rows in smem, M=128, N=64, K=8) -> tcgen05.commit per chunk; each frees
+//                the operand tile after its last chunk
 //   warps 8-23   epilogue (warp w: TMEM lanes 32*(w%4).., 16 of the tile's 64 rows): tcgen05.ld each
 //                chunk result as soon as it is complete (handing its columns straight back to the
 //                MMA warp), add, then run the fused stage (EPI); setmaxnreg moves the producers'
@@ -87,6 +89,10 @@ constexpr int EPI_GROUPS = EPI_ROWS / 8;
 constexpr int NT = (W_EPI + EPI_WARPS) * 32;
 constexpr int REGS_PRODUCER = 32, REGS_EPI = 104;    // must fit the launch allocation (768 x 80 = 61440): 256 x 32 + 512 x 104 = 61440
 constexpr int NCONS = EPI_WARPS * 32;
+#ifndef DGMK_LG_ISSUERS
+#define DGMK_LG_ISSUERS 2
+#endif
+constexpr int NISS = DGMK_LG_ISSUERS;   // MMA issuer warps (warps 1 .. NISS), chunk c belongs to issuer c % NISS
 constexpr int TMEM_COLS = 512;
 constexpr int TM_WHI = 0, TM_WLO = KTOT, TM_ACC = 2 * KTOT;   // TMEM column map
 
@@ -212,7 +218,7 @@ __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restric
     }
     for (int s = 0; s < X_STAGES; ++s) {
       tc::mbar_init(OP_FULL + 8 * s, NTW);
-      tc::mbar_init(OP_EMPTY + 8 * s, 1);      // tcgen05.commit
+      tc::mbar_init(OP_EMPTY + 8 * s, NISS);   // tcgen05.commit of every issuer
     }
     for (int c = 0; c < NCH; ++c) {
       tc::mbar_init(TC_FULL + 8 * c, 1);       // tcgen05.commit
@@ -276,8 +282,8 @@ __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restric
       lg_prof[2] = i;
 #endif
       LG_PROF_OUT(0);
-    } else if (warp == 1) {
-      // ================================ MMA issuer =========================================
+    } else if (warp <= NISS) {
+      // ================================ MMA issuer(s) ======================================
       // the whole warp runs the loop (uniform control flow); one elected lane issues
       uint32_t i = 0;
       LG_PROF_DECL;
@@ -288,7 +294,7 @@ __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restric
         LG_ADD(1, t1);
         const uint32_t xb = tc::smem_u32(smem + X_OFF + ts * X_STAGE_BYTES);
 #pragma unroll 1   // this warp lives on 40 registers (setmaxnreg): one chunk's descriptors at a time
-        for (int c = 0; c < NCH; ++c) {
+        for (int c = warp - 1; c < NCH; c += NISS) {
           LG_T(t0);
           tc::mbar_wait(TC_EMPTY + 8 * c, (i & 1) ^ 1);   // epilogue has read the previous tile's chunk c
           LG_ADD(0, t0);
@@ -312,13 +318,13 @@ __global__ void __launch_bounds__(NT, 1) lane_gemm_kernel(const float* __restric
               }
             }
             tc::mma_commit(TC_FULL + 8 * c);                        // chunk result complete
-            if (c == NCH - 1) tc::mma_commit(OP_EMPTY + 8 * ts);    // operand tile reusable once all its MMAs have read it
+            if (c + NISS >= NCH) tc::mma_commit(OP_EMPTY + 8 * ts);   // operand tile reusable once all MMAs (of every issuer) have read it
           }
           __syncwarp();
           LG_ADD(2, t2);
         }
       }
-      LG_PROF_OUT(8);
+      if (warp == 1) { LG_PROF_OUT(8); }
     }
    } else if (warp < W_EPI) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS_PRODUCER));
