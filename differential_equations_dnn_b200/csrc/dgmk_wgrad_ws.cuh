@@ -71,6 +71,9 @@ constexpr int HR = KC / 2;                         // rows of a chunk per loader
 constexpr int REGS_LOAD = 72, REGS_STAGE = 96, REGS_DRAIN = 120;   // 256*72 + 128*96 + 256*120 = 640*96
 // SEP: launch allocation 768 x 80 = 61440 = 256*64 + 128*96 + 256*112 + 128*32
 constexpr int REGS_LOAD_SEP = 64, REGS_DRAIN_SEP = 112, REGS_ISSUE_SEP = 32;
+#ifndef DGMK_WG_ISSUERS
+#define DGMK_WG_ISSUERS 1   // 2: a second issuer warp on alternate chunks -- measured in the step: 18.7 -> 18.3-18.7 ms, within the noise
+#endif
 constexpr int NB = 3;                              // S ring stages
 constexpr int STAGE_BYTES = 2 * TN_OPER_BYTES;     // hi | lo
 constexpr int BAR_OFF = NB * STAGE_BYTES;
@@ -435,10 +438,12 @@ __global__ void __launch_bounds__(SEP ? NT_SEP : NT, 1) wgrad_ws_kernel(const fl
     } else {
       // ============================== SEP: MMA issuer (warp 20; 21-23 only hand their registers over) ===
       asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS_ISSUE_SEP));
-      if (warp == W_ISSUE) {
+      if (warp == W_ISSUE || (DGMK_WG_ISSUERS == 2 && warp == W_ISSUE + 2)) {
+        // (DGMK_WG_ISSUERS == 2: issuers on alternate chunks, issuer i owns A buffer i and accumulator buffer i.  It pays
+        // in the data-gradient and lane kernels, not here: loaders and stagers, not the issuer, set this kernel's pace)
 #pragma unroll 1
-        for (int64_t c = 0; c < nchunks; ++c) issue(c);
-        WG_OUT(16);
+        for (int64_t c = (warp - W_ISSUE) >> 1; c < nchunks; c += DGMK_WG_ISSUERS) issue(c);
+        if (warp == W_ISSUE) { WG_OUT(16); }
       } else if (warp == W_ISSUE + 1) {
         // bulk-copy producer: raw S tile of chunk c -> ring stage (rows of S are contiguous when LDS == 128)
         int rs = 0; uint32_t ruse = 0;
