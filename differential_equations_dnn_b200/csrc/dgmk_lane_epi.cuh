@@ -81,12 +81,12 @@ struct DgmFwd1Epi {
   using Tile = XTile<C>;
   struct State {};
   __device__ __forceinline__ void finish(const State&, const Const&, int) const {}
-  struct Pre { XPre<C> x; float s[8]; };
+  struct Pre { float s[8]; };   // (the coordinates are picked up by shuffle inside apply(): they sit in registers, and
+                                // a prefetched copy per group in flight cost the value-row kernels 16 registers each)
   __device__ __forceinline__ Const init(int gate, int j) const { Const k; k.u = ub[gate * HP + j]; k.gate = gate; k.j = j; return k; }
   __device__ __forceinline__ void tile(Tile& t, const Const&, int64_t row0, int64_t M, int lane) const { t.load(xs, row0, M, lane); }
   template <bool FULL>
   __device__ __forceinline__ void prefetch(Pre& p, const Tile& t, const Const& k, int64_t row0, int cg, int64_t M) const {
-    p.x.load(t, cg);
     if (k.gate == 2) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) p.s[q] = ldg_f(S + clampr<FULL>(row0 + q, M) * HP + k.j);
@@ -95,12 +95,14 @@ struct DgmFwd1Epi {
   template <bool FULL>
   __device__ __forceinline__ void apply(const Pre& p, State& st, const Tile& t, int cg, const Const& k, int64_t row0, int64_t M, const float (&acc)[8]) const {
     float af[8], sr[8];   // a-form rows and (R gate) s*R rows of the whole group
+    XPre<C> px;
+    px.load(t, cg);
 #pragma unroll
     for (int pp = 0; pp < 8 / C; ++pp) {
       float a[C], y[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) a[c] = acc[pp * C + c];
-      add_input_map_xy<CS>(a, k.u, p.x.x0[pp], p.x.x1[pp], xs.d);
+      add_input_map_xy<CS>(a, k.u, px.x0[pp], px.x1[pp], xs.d);
       act_fwd<CS, ACT>(a, y);
       af[pp * C] = y[0];
 #pragma unroll
@@ -136,12 +138,11 @@ struct DgmFwd2Epi {
   using Tile = XTile<C>;
   struct State {};
   __device__ __forceinline__ void finish(const State&, const Const&, int) const {}
-  struct Pre { XPre<C> x; float z[8], g[8], s[8]; };
+  struct Pre { float z[8], g[8], s[8]; };
   __device__ __forceinline__ Const init(int, int j) const { Const k; k.u = ub[3 * HP + j]; k.j = j; return k; }
   __device__ __forceinline__ void tile(Tile& t, const Const&, int64_t row0, int64_t M, int lane) const { t.load(xs, row0, M, lane); }
   template <bool FULL>
   __device__ __forceinline__ void prefetch(Pre& p, const Tile& t, const Const& k, int64_t row0, int cg, int64_t M) const {
-    p.x.load(t, cg);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int64_t r = clampr<FULL>(row0 + q, M);
@@ -154,12 +155,14 @@ struct DgmFwd2Epi {
   template <bool FULL>
   __device__ __forceinline__ void apply(const Pre& p, State& st, const Tile& t, int cg, const Const& k, int64_t row0, int64_t M, const float (&acc)[8]) const {
     float af[8], sn[8];
+    XPre<C> px;
+    px.load(t, cg);
 #pragma unroll
     for (int pp = 0; pp < 8 / C; ++pp) {
       float a[C], h[C], z[C], g[C], s[C], t1[C], t2[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) { a[c] = acc[pp * C + c]; t1[c] = p.z[pp * C + c]; t2[c] = p.g[pp * C + c]; s[c] = p.s[pp * C + c]; }
-      add_input_map_xy<CS>(a, k.u, p.x.x0[pp], p.x.x1[pp], xs.d);
+      add_input_map_xy<CS>(a, k.u, px.x0[pp], px.x1[pp], xs.d);
       act_fwd<CS, ACT>(a, h);
       af[pp * C] = h[0];
 #pragma unroll
