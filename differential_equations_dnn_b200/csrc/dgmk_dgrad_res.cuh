@@ -210,8 +210,23 @@ __global__ void __launch_bounds__(NT, 1) dgrad_res_kernel(const __grid_constant_
       // overtakes loads still queued in the shared-memory pipe, the copy thread sees the stage free and the next tensor
       // copy lands on top of the last piece before it has been read (measured: exactly that piece carried the data of
       // chunk g + 2 in ~1000 of 4.8 M results, only in the MMA-bound steady state).  The fence orders the loads first.
+#ifndef DGMK_DG_PRED_RELEASE
       asm volatile("fence.acq_rel.cta;\n" ::: "memory");
       lg::mbar_arrive(RAW_EMPTY + 8 * wg);
+#else
+      {   // alternative, measured equal (1.105 against 1.095 ms): exactly one of two predicated arrives executes, and the
+          // predicate depends on a word of every load, so neither can issue before the loads have written their registers
+          // (ptxas keeps both; a data dependence it can fold -- and t, x, 0 -- it removes)
+        const uint32_t dep = __float_as_uint(x[0].x) ^ __float_as_uint(x[1].y) ^ __float_as_uint(x[2].z) ^ __float_as_uint(x[3].w) ^
+                             __float_as_uint(x[4].x) ^ __float_as_uint(x[5].y) ^ __float_as_uint(x[6].z) ^ __float_as_uint(x[7].w);
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0x5bd1e995;\n\t"
+            "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t"
+            "@!p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}\n" ::"r"(RAW_EMPTY + 8 * wg),
+            "r"(dep)
+            : "memory");
+      }
+#endif
       DG_ADD(1, t1);
       DG_T(t2);
       tc::mbar_wait(A_EMPTY + 8 * rs, (ur & 1) ^ 1);   // the MMAs of round R - 2 have read this slot
