@@ -676,7 +676,7 @@ def roofline(lib, wl, prof, B, ms_step, dev):
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr):
             tj = json.load(open(tr))
-            key = {0: "wgrad_ws", 1: "lane_gemm", 2: "gemm_nn_tc", 5: "tile_step"}.get(dom)
+            key = {0: "wgrad_ws", 1: "lane_gemm", 2: "dgrad_res", 5: "tile_step"}.get(dom)
             ratio = tj.get(key + "_dram_over_algorithmic") if key else None
             if ratio is not None:   # ncu dram__bytes_read+write per launch / design bytes of that launch
                 roof["traffic"] = ratio * roof["launch"]["design_bytes"]
